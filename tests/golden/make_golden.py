@@ -64,7 +64,7 @@ def put_dict(out, prefix, d):
 
     for k, v in d.items():
         if isinstance(v, torch.Tensor):
-            out["{}/{}".format(prefix, k)] = v.detach().cpu().numpy()
+            out["{}/{}".format(prefix, k)] = v.detach().cpu().numpy().copy()
         elif isinstance(v, (bool, int, float)):
             out["{}/{}".format(prefix, k)] = np.array(v)
 

@@ -1,0 +1,224 @@
+// AAE sparse ends (reference src/models/ae.py:98-157):
+//   encoder first layer  = CSR SpMM over the batch rows with bias + tanh fused (ae.py:101-110)
+//   decoder last layer   = row-gather SDDMM  o_f = A3[r_f] . W4[c_f] + b4[c_f]  fused with the loss, its
+//                          derivative, and the first backward product dZ3 = (G W4) * (1 - A3^2)  (ae.py:135-156)
+// Both read every weight row with 128-bit coalesced loads (one 1 KB row of H=256 floats = 2 float4 per lane).
+// Roofline: HBM/L2 bytes — per target 4*H (W4 row) + 16 B; per data entry 4*H + 8 B.
+#include "kernels.cuh"
+
+namespace dmt {
+
+// One block per batch row, one thread per hidden unit.
+__global__ void __launch_bounds__(512) ae_encoder_fwd_kernel(const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ indices,
+                                                            const float* __restrict__ val,
+                                                            const float* __restrict__ W1t,
+                                                            const float* __restrict__ b1, int H,
+                                                            float* __restrict__ A1, BatchRef br) {
+    int lo, hi;
+    if (!batch_range(br, lo, hi)) return;
+    int j = blockIdx.x;
+    if (j >= hi - lo) return;
+    int u = rows[lo + j];
+    int e0 = indptr[u], e1 = indptr[u + 1];
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float acc = 0.f;
+        int e = e0;
+        for (; e + 4 <= e1; e += 4) {  // 4 independent row loads in flight
+            int c0 = indices[e], c1 = indices[e + 1], c2 = indices[e + 2], c3 = indices[e + 3];
+            float v0 = val[e], v1 = val[e + 1], v2 = val[e + 2], v3 = val[e + 3];
+            float w0 = W1t[(int64_t)c0 * H + h], w1 = W1t[(int64_t)c1 * H + h];
+            float w2 = W1t[(int64_t)c2 * H + h], w3 = W1t[(int64_t)c3 * H + h];
+            acc = fmaf(v0, w0, acc);
+            acc = fmaf(v1, w1, acc);
+            acc = fmaf(v2, w2, acc);
+            acc = fmaf(v3, w3, acc);
+        }
+        for (; e < e1; ++e) acc = fmaf(val[e], W1t[(int64_t)indices[e] * H + h], acc);
+        A1[(int64_t)j * H + h] = tanhf(acc + b1[h]);
+    }
+}
+
+// One block (8 warps) per batch row. VEC = H / 128: each lane owns VEC float4 slices of the hidden vector.
+template <int VEC>
+__global__ void __launch_bounds__(256) ae_decoder_fwd_kernel(const int32_t* __restrict__ rows,
+                                                            const int32_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ indices,
+                                                            const float* __restrict__ target,
+                                                            const float* __restrict__ A3,
+                                                            const float* __restrict__ W4,
+                                                            const float* __restrict__ b4, int loss_kind,
+                                                            const int32_t* __restrict__ n_targets,
+                                                            const int32_t* __restrict__ ent_off,
+                                                            float* __restrict__ pred, float* __restrict__ gout,
+                                                            float* __restrict__ dZ3, float* __restrict__ loss_rows,
+                                                            BatchRef br) {
+    constexpr int H = VEC * 128;
+    __shared__ float s_acc[8][H];
+    __shared__ float s_loss[8];
+    int lo, hi;
+    if (!batch_range(br, lo, hi)) return;
+    int j = blockIdx.x;
+    if (j >= hi - lo) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int u = rows[lo + j];
+    const int e0 = indptr[u], e1 = indptr[u + 1];
+    const bool train = gout != nullptr;
+    const float inv_n = train ? 1.f / (float)n_targets[br.row_off ? br.b : 0] : 0.f;
+    const int64_t out_base = ent_off ? (int64_t)ent_off[lo + j] - e0 : 0;  // entry e is written at out_base + e
+    float4 a[VEC], acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        a[v] = ld4(A3 + (int64_t)j * H + v * 128 + lane * 4);
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float loss_acc = 0.f;
+    // each warp takes 32-entry chunks; the chunk's columns/targets are loaded coalesced, then broadcast
+    for (int eb = e0 + wid * 32; eb < e1; eb += 8 * 32) {
+        int e = eb + lane;
+        int c_l = 0;
+        float y_l = 0.f;
+        if (e < e1) {
+            c_l = indices[e];
+            y_l = target ? target[e] : 0.f;
+        }
+        int cnt = min(32, e1 - eb);
+        float o_l = 0.f;  // lane i keeps the prediction of entry eb+i
+        int i = 0;
+        for (; i + 2 <= cnt; i += 2) {  // two rows in flight per warp
+            int c0 = __shfl_sync(0xffffffffu, c_l, i), c1 = __shfl_sync(0xffffffffu, c_l, i + 1);
+            float4 w0[VEC], w1[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                w0[v] = ld4(W4 + (int64_t)c0 * H + v * 128 + lane * 4);
+                w1[v] = ld4(W4 + (int64_t)c1 * H + v * 128 + lane * 4);
+            }
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                d0 += a[v].x * w0[v].x + a[v].y * w0[v].y + a[v].z * w0[v].z + a[v].w * w0[v].w;
+                d1 += a[v].x * w1[v].x + a[v].y * w1[v].y + a[v].z * w1[v].z + a[v].w * w1[v].w;
+            }
+            d0 = warp_sum(d0) + b4[c0];
+            d1 = warp_sum(d1) + b4[c1];
+            if (lane == i) o_l = d0;
+            if (lane == i + 1) o_l = d1;
+            if (train) {
+                float g0 = loss_grad(loss_kind, d0, __shfl_sync(0xffffffffu, y_l, i)) * inv_n;
+                float g1 = loss_grad(loss_kind, d1, __shfl_sync(0xffffffffu, y_l, i + 1)) * inv_n;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    acc[v].x += g0 * w0[v].x + g1 * w1[v].x;
+                    acc[v].y += g0 * w0[v].y + g1 * w1[v].y;
+                    acc[v].z += g0 * w0[v].z + g1 * w1[v].z;
+                    acc[v].w += g0 * w0[v].w + g1 * w1[v].w;
+                }
+            }
+        }
+        for (; i < cnt; ++i) {
+            int c0 = __shfl_sync(0xffffffffu, c_l, i);
+            float4 w0[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) w0[v] = ld4(W4 + (int64_t)c0 * H + v * 128 + lane * 4);
+            float d0 = 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) d0 += a[v].x * w0[v].x + a[v].y * w0[v].y + a[v].z * w0[v].z + a[v].w * w0[v].w;
+            d0 = warp_sum(d0) + b4[c0];
+            if (lane == i) o_l = d0;
+            if (train) {
+                float g0 = loss_grad(loss_kind, d0, __shfl_sync(0xffffffffu, y_l, i)) * inv_n;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    acc[v].x += g0 * w0[v].x;
+                    acc[v].y += g0 * w0[v].y;
+                    acc[v].z += g0 * w0[v].z;
+                    acc[v].w += g0 * w0[v].w;
+                }
+            }
+        }
+        if (e < e1) {  // coalesced write-back of the chunk
+            if (pred) pred[out_base + e] = o_l;
+            if (train) {
+                gout[out_base + e] = loss_grad(loss_kind, o_l, y_l) * inv_n;
+                loss_acc += loss_value(loss_kind, o_l, y_l);
+            }
+        }
+    }
+    if (!train) return;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) st4(&s_acc[wid][v * 128 + lane * 4], acc[v]);
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0) s_loss[wid] = loss_acc;
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_acc[w][h];
+        float av = A3[(int64_t)j * H + h];
+        dZ3[(int64_t)j * H + h] = s * (1.f - av * av);
+    }
+    if (threadIdx.x == 0) {
+        float l = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) l += s_loss[w];
+        loss_rows[j] = l;
+    }
+}
+
+int launch_ae_encoder_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* val,
+                          const float* W1t, const float* b1, int H, float* A1, int n_rows_max, BatchRef br,
+                          cudaStream_t st) {
+    if (n_rows_max <= 0) return 0;
+    int threads = H >= 512 ? 512 : (H + 31) / 32 * 32;
+    ae_encoder_fwd_kernel<<<n_rows_max, threads, 0, st>>>(rows, indptr, indices, val, W1t, b1, H, A1, br);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
+                          const float* A3, const float* W4, const float* b4, int H, int loss_kind,
+                          const int32_t* n_targets, const int32_t* ent_off, float* pred, float* gout, float* dZ3,
+                          float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st) {
+    if (n_rows_max <= 0) return 0;
+#define DMT_DEC(V)                                                                                              \
+    ae_decoder_fwd_kernel<V><<<n_rows_max, 256, 0, st>>>(rows, indptr, indices, target, A3, W4, b4, loss_kind, \
+                                                         n_targets, ent_off, pred, gout, dZ3, loss_rows, br)
+    if (H == 128) DMT_DEC(1);
+    else if (H == 256) DMT_DEC(2);
+    else if (H == 384) DMT_DEC(3);
+    else if (H == 512) DMT_DEC(4);
+    else {
+        set_error("decoder hidden size must be 128, 256, 384 or 512");
+        return DMT_E_ARG;
+    }
+#undef DMT_DEC
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dmt
+
+using namespace dmt;
+
+extern "C" {
+
+int dmt_ae_encoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices,
+                       const float* val, const float* W1t, const float* b1, int H, float* A1, void* stream) {
+    DMT_REQUIRE(n_rows >= 0 && H > 0, "dmt_ae_encoder_fwd: bad argument");
+    return launch_ae_encoder_fwd(rows, indptr, indices, val, W1t, b1, H, A1, n_rows, batch_by_value(0, n_rows),
+                                 as_stream(stream));
+}
+
+int dmt_ae_decoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices,
+                       const float* target, const float* A3, const float* W4, const float* b4, int H, int loss_kind,
+                       const int32_t* n_targets, float* pred, float* gout, float* dZ3, float* loss_rows,
+                       void* stream) {
+    DMT_REQUIRE(n_rows >= 0, "dmt_ae_decoder_fwd: bad argument");
+    DMT_REQUIRE(gout == nullptr || (n_targets && dZ3 && loss_rows && target), "dmt_ae_decoder_fwd: train mode needs "
+                "n_targets, target, dZ3 and loss_rows");
+    return launch_ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, H, loss_kind, n_targets, nullptr, pred,
+                                 gout, dZ3, loss_rows, n_rows, batch_by_value(0, n_rows), as_stream(stream));
+}
+
+}  // extern "C"

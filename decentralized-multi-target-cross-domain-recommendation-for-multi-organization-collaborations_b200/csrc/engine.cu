@@ -1,0 +1,516 @@
+// Device-resident organization engine: Organization.train / Organization.predict of the reference
+// (src/organization.py:140-217) for the AAE, with the batch loop moved onto the device.
+//
+// Per local epoch (one call):
+//   plan   : from the epoch's row order build, for targets and data, the batch-ordered entry space, its stable
+//            sort by (batch, column) and the (batch, column) segments  -> no per-batch host work at all
+//   steps  : for every batch one fixed sequence of 17 kernels + 1 memset (forward, fused decoder/loss/first
+//            backward product, segmented gradient reductions, dense backward, global-norm clip + Adam); every
+//            kernel reads its batch bounds from device memory, so the whole epoch is ONE CUDA graph that is
+//            captured once and replayed for every epoch of every round.
+// Organizations own private streams: the per-organization graphs of one rank run concurrently and fill the
+// 148 SMs even though a single 500-row batch cannot.
+#include <cub/cub.cuh>
+
+#include <new>
+
+#include "kernels.cuh"
+
+namespace dmt {
+
+struct PlanSide {  // per-matrix (targets or data) epoch plan buffers
+    int64_t cap = 0;                // entry capacity
+    int32_t* ent_off = nullptr;     // [rows_cap + 1] offsets of each batch-row in the batch-ordered entry space
+    int32_t* len = nullptr;         // [rows_cap + 1]
+    uint32_t* key = nullptr;        // [cap] batch * n_cols + col
+    int32_t* ent_row = nullptr;     // [cap] row index inside its batch
+    int32_t* perm = nullptr;        // [cap] entry ids sorted by key (stable)
+    int32_t* seg_key = nullptr;     // [cap]
+    int32_t* seg_off = nullptr;     // [cap + 1]
+    int32_t* n_seg = nullptr;       // [1]
+    int32_t* batch_seg_off = nullptr;  // [nb_cap + 1]
+    int32_t* batch_cnt = nullptr;   // [nb_cap] entries per batch
+};
+
+}  // namespace dmt
+
+using namespace dmt;
+
+struct dmt_org {
+    int n_rows, n_enc, n_dec, H1, H2, batch_rows, loss_kind;
+    cudaStream_t st;
+    bool own_stream;
+    const int32_t *d_indptr, *d_indices, *t_indptr, *t_indices;
+    const float *d_val, *t_val;
+    int64_t d_nnz, t_nnz;
+    // flat parameter / gradient / moment buffers and sub-views
+    int64_t n_params;
+    float *P, *G, *M, *V;
+    int64_t oW1, ob1, oW2, ob2, oW3, ob3, oW4, ob4;
+    // activations
+    int act_rows;
+    float *a1, *a2, *c, *a3, *dz3, *dz2, *dz1, *loss_rows;
+    int32_t* iota_rows;
+    // plan
+    int rows_cap, nb_cap;
+    PlanSide pt, pd;
+    float* gbuf;      // [t cap] dL/do per target entry (batch-ordered)
+    float* dval_ord;  // [d cap] data values in batch-ordered entry space
+    int32_t* row_batch;  // [rows_cap]
+    int32_t* active;     // [nb_cap]
+    void* sort_temp;
+    int64_t sort_temp_bytes;
+    // epoch inputs (stable addresses for the graph)
+    int32_t* rows_buf;     // [rows_cap]
+    int32_t* row_off_buf;  // [nb_cap + 1]
+    uint8_t* keep_buf;     // [rows_cap * H2]
+    uint64_t* seed_dev;
+    float* loss_buf;  // [nb_cap]
+    // optimizer scalars
+    float* partial;
+    AdamScalars* sc;
+    int* step_dev;
+    cudaEvent_t ev;
+    // graph cache
+    cudaGraphExec_t exec;
+    int g_nb, g_keep;
+    AdamHyper g_hp;
+};
+
+namespace dmt {
+
+static int free_all(dmt_org* o);
+
+template <class T>
+static int dalloc(T** p, int64_t n) {
+    if (n < 1) n = 1;
+    DMT_CUDA(cudaMalloc(reinterpret_cast<void**>(p), (size_t)n * sizeof(T)));
+    return 0;
+}
+
+static int alloc_side(PlanSide& s, int64_t cap, int rows_cap, int nb_cap) {
+    s.cap = cap;
+    int rc = 0;
+    if ((rc = dalloc(&s.ent_off, rows_cap + 2))) return rc;
+    if ((rc = dalloc(&s.len, rows_cap + 2))) return rc;
+    if ((rc = dalloc(&s.key, cap))) return rc;
+    if ((rc = dalloc(&s.ent_row, cap))) return rc;
+    if ((rc = dalloc(&s.perm, cap))) return rc;
+    if ((rc = dalloc(&s.seg_key, cap))) return rc;
+    if ((rc = dalloc(&s.seg_off, cap + 2))) return rc;
+    if ((rc = dalloc(&s.n_seg, 1))) return rc;
+    if ((rc = dalloc(&s.batch_seg_off, nb_cap + 2))) return rc;
+    if ((rc = dalloc(&s.batch_cnt, nb_cap + 1))) return rc;
+    return 0;
+}
+
+static void free_side(PlanSide& s) {
+    cudaFree(s.ent_off); cudaFree(s.len); cudaFree(s.key); cudaFree(s.ent_row); cudaFree(s.perm);
+    cudaFree(s.seg_key); cudaFree(s.seg_off); cudaFree(s.n_seg); cudaFree(s.batch_seg_off); cudaFree(s.batch_cnt);
+}
+
+// ---------------------------------------------------------------- plan kernels
+__global__ void plan_row_len_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ row_off, int nb,
+                                    int n, const int32_t* __restrict__ t_indptr,
+                                    const int32_t* __restrict__ d_indptr, int32_t* __restrict__ tlen,
+                                    int32_t* __restrict__ dlen, int32_t* __restrict__ row_batch) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n) return;
+    if (j == n) {  // terminator for the exclusive scan
+        tlen[j] = 0;
+        dlen[j] = 0;
+        return;
+    }
+    int u = rows[j];
+    tlen[j] = t_indptr[u + 1] - t_indptr[u];
+    dlen[j] = d_indptr[u + 1] - d_indptr[u];
+    int lo = 0, hi = nb;  // batch of row j: largest b with row_off[b] <= j
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (row_off[mid] <= j) lo = mid; else hi = mid;
+    }
+    row_batch[j] = lo;
+}
+
+__global__ void plan_batch_meta_kernel(const int32_t* __restrict__ row_off, int nb,
+                                       const int32_t* __restrict__ t_off, const int32_t* __restrict__ d_off,
+                                       int32_t* __restrict__ t_cnt, int32_t* __restrict__ d_cnt,
+                                       int32_t* __restrict__ active) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    int r0 = row_off[b], r1 = row_off[b + 1];
+    t_cnt[b] = t_off[r1] - t_off[r0];
+    d_cnt[b] = d_off[r1] - d_off[r0];
+    // a batch without DATA entries is skipped entirely (reference src/organization.py:153-155)
+    active[b] = d_cnt[b] > 0 ? 1 : 0;
+}
+
+// one warp per batch-row: writes the (batch, column) keys and the in-batch row index of every entry
+__global__ void __launch_bounds__(256) plan_fill_kernel(const int32_t* __restrict__ rows,
+                                                        const int32_t* __restrict__ row_off,
+                                                        const int32_t* __restrict__ row_batch, int n,
+                                                        const int32_t* __restrict__ indptr,
+                                                        const int32_t* __restrict__ indices,
+                                                        const float* __restrict__ val, int n_cols,
+                                                        const int32_t* __restrict__ ent_off,
+                                                        uint32_t* __restrict__ key, int32_t* __restrict__ ent_row,
+                                                        float* __restrict__ val_ord) {
+    int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (j >= n) return;
+    int u = rows[j], b = row_batch[j];
+    int s = indptr[u], len = indptr[u + 1] - s, o = ent_off[j];
+    int rin = j - row_off[b];
+    for (int k = lane; k < len; k += 32) {
+        key[o + k] = (uint32_t)b * (uint32_t)n_cols + (uint32_t)indices[s + k];
+        ent_row[o + k] = rin;
+        if (val_ord != nullptr) val_ord[o + k] = val[s + k];
+    }
+}
+
+__global__ void plan_batch_seg_kernel(const int32_t* __restrict__ seg_key, const int32_t* __restrict__ n_seg, int nb,
+                                      int n_cols, int32_t* __restrict__ batch_seg_off) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
+    int ns = n_seg[0];
+    uint32_t bound = (uint32_t)b * (uint32_t)n_cols;
+    int lo = 0, hi = ns;  // first segment with key >= bound
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((uint32_t)seg_key[mid] < bound) lo = mid + 1; else hi = mid;
+    }
+    batch_seg_off[b] = lo;
+}
+
+static int bits_for(int64_t bound) {
+    int bits = 1;
+    while (bits < 32 && (1LL << bits) < bound) ++bits;
+    return bits;
+}
+
+static int scan_lengths(dmt_org* o, PlanSide& s, int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, s.len, s.ent_off, n + 1);
+    if ((int64_t)bytes > o->sort_temp_bytes) {
+        set_error("plan: scan temp too small");
+        return DMT_E_STATE;
+    }
+    DMT_CUDA(cub::DeviceScan::ExclusiveSum(o->sort_temp, bytes, s.len, s.ent_off, n + 1, o->st));
+    return 0;
+}
+
+static int build_plan(dmt_org* o, int n, int nb, int64_t n_t, int64_t n_d) {
+    cudaStream_t st = o->st;
+    plan_row_len_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(o->rows_buf, o->row_off_buf, nb, n, o->t_indptr,
+                                                            o->d_indptr, o->pt.len, o->pd.len, o->row_batch);
+    DMT_LAUNCH_CHECK();
+    int rc;
+    if ((rc = scan_lengths(o, o->pt, n))) return rc;
+    if ((rc = scan_lengths(o, o->pd, n))) return rc;
+    plan_batch_meta_kernel<<<(nb + 127) / 128, 128, 0, st>>>(o->row_off_buf, nb, o->pt.ent_off, o->pd.ent_off,
+                                                            o->pt.batch_cnt, o->pd.batch_cnt, o->active);
+    DMT_LAUNCH_CHECK();
+    int blocks = (n + 7) / 8;
+    if (blocks > 0) {
+        plan_fill_kernel<<<blocks, 256, 0, st>>>(o->rows_buf, o->row_off_buf, o->row_batch, n, o->t_indptr,
+                                                o->t_indices, nullptr, o->n_dec, o->pt.ent_off, o->pt.key,
+                                                o->pt.ent_row, nullptr);
+        DMT_LAUNCH_CHECK();
+        plan_fill_kernel<<<blocks, 256, 0, st>>>(o->rows_buf, o->row_off_buf, o->row_batch, n, o->d_indptr,
+                                                o->d_indices, o->d_val, o->n_enc, o->pd.ent_off, o->pd.key,
+                                                o->pd.ent_row, o->dval_ord);
+        DMT_LAUNCH_CHECK();
+    }
+    if ((rc = sort_segments(o->pt.key, n_t, bits_for((int64_t)nb * o->n_dec), o->pt.perm, o->pt.seg_key,
+                            o->pt.seg_off, o->pt.n_seg, o->sort_temp, o->sort_temp_bytes, st)))
+        return rc;
+    if ((rc = sort_segments(o->pd.key, n_d, bits_for((int64_t)nb * o->n_enc), o->pd.perm, o->pd.seg_key,
+                            o->pd.seg_off, o->pd.n_seg, o->sort_temp, o->sort_temp_bytes, st)))
+        return rc;
+    plan_batch_seg_kernel<<<(nb + 1 + 127) / 128, 128, 0, st>>>(o->pt.seg_key, o->pt.n_seg, nb, o->n_dec,
+                                                               o->pt.batch_seg_off);
+    DMT_LAUNCH_CHECK();
+    plan_batch_seg_kernel<<<(nb + 1 + 127) / 128, 128, 0, st>>>(o->pd.seg_key, o->pd.n_seg, nb, o->n_enc,
+                                                               o->pd.batch_seg_off);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------- one training step (enqueue only)
+static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp) {
+    cudaStream_t st = o->st;
+    const int B = o->batch_rows, H1 = o->H1, H2 = o->H2;
+    BatchRef br{o->row_off_buf, o->active, b, 0, 0};
+    float *W1t = o->P + o->oW1, *b1 = o->P + o->ob1, *W2 = o->P + o->oW2, *b2 = o->P + o->ob2;
+    float *W3 = o->P + o->oW3, *b3 = o->P + o->ob3, *W4 = o->P + o->oW4, *b4 = o->P + o->ob4;
+    float* G = o->G;
+    int rc;
+    // keep bytes of batch b start at row row_off[b]; the dense epilogue adds that base itself (replayable graph).
+    Dropout drop;
+    drop.keep = use_keep ? o->keep_buf : nullptr;
+    drop.seed_dev = o->seed_dev;
+    drop.step_dev = o->step_dev;
+    drop.row_base = o->row_off_buf;
+    drop.b = b;
+    drop.scale = 2.0f;  // nn.Dropout(p=0.5), reference src/models/ae.py:81
+    drop.p = 0.5f;
+    drop.enabled = 1;
+    Dropout nodrop;
+    // forward
+    if ((rc = launch_ae_encoder_fwd(o->rows_buf, o->d_indptr, o->d_indices, o->d_val, W1t, b1, H1, o->a1, B, br, st)))
+        return rc;
+    if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, o->a2, drop, B, H2, H1, 1, br, st))) return rc;
+    if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, B, H1, H2, 1, br, st))) return rc;
+    DMT_CUDA(cudaMemsetAsync(G, 0, (size_t)o->n_params * sizeof(float), st));
+    // decoder + loss + dZ3
+    if ((rc = launch_ae_decoder_fwd(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1, DMT_LOSS_MSE,
+                                    o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, o->dz3, o->loss_rows, B, br,
+                                    st)))
+        return rc;
+    // dW4, db4: segmented over (batch, target column)
+    SegRef st4{o->pt.batch_seg_off, nullptr, b, 0, 0, o->n_dec};
+    if ((rc = launch_segment_reduce_rows(o->pt.perm, o->pt.seg_key, o->pt.seg_off, st4, o->n_dec, o->gbuf,
+                                         o->pt.ent_row, o->a3, H1, G + o->oW4, G + o->ob4, o->active, st)))
+        return rc;
+    // dense backward
+    if ((rc = launch_dense_bwd_w(o->dz3, o->c, G + o->oW3, G + o->ob3, B, H1, H2, br, st))) return rc;
+    if ((rc = launch_dense_bwd_x(o->dz3, W3, o->a2, drop, o->dz2, B, H1, H2, 1, br, st))) return rc;
+    if ((rc = launch_dense_bwd_w(o->dz2, o->a1, G + o->oW2, G + o->ob2, B, H2, H1, br, st))) return rc;
+    if ((rc = launch_dense_bwd_x(o->dz2, W2, o->a1, nodrop, o->dz1, B, H2, H1, 1, br, st))) return rc;
+    // dW1t: segmented over (batch, data column); db1 = column sums of dZ1
+    SegRef sd{o->pd.batch_seg_off, nullptr, b, 0, 0, o->n_enc};
+    if ((rc = launch_segment_reduce_rows(o->pd.perm, o->pd.seg_key, o->pd.seg_off, sd, o->n_enc, o->dval_ord,
+                                         o->pd.ent_row, o->dz1, H1, G + o->oW1, nullptr, o->active, st)))
+        return rc;
+    if ((rc = launch_colsum(o->dz1, H1, G + o->ob1, br, st))) return rc;
+    // clip + Adam
+    if ((rc = launch_sqnorm_stage1(G, o->n_params, o->partial, br, st))) return rc;
+    if ((rc = launch_adam_prepare(o->partial, kNormBlocks, nullptr, nullptr, o->sc, hp, 0, o->step_dev, o->loss_rows,
+                                  o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
+        return rc;
+    if ((rc = launch_adam(o->P, G, o->M, o->V, o->n_params, o->sc, hp, st))) return rc;
+    return 0;
+}
+
+static bool same_hp(const AdamHyper& a, const AdamHyper& b) {
+    return a.lr == b.lr && a.beta1 == b.beta1 && a.beta2 == b.beta2 && a.eps == b.eps &&
+           a.weight_decay == b.weight_decay && a.max_norm == b.max_norm;
+}
+
+static int free_all(dmt_org* o) {
+    if (o->exec) cudaGraphExecDestroy(o->exec);
+    cudaFree(o->P); cudaFree(o->G); cudaFree(o->M); cudaFree(o->V);
+    cudaFree(o->a1); cudaFree(o->a2); cudaFree(o->c); cudaFree(o->a3); cudaFree(o->dz3); cudaFree(o->dz2);
+    cudaFree(o->dz1); cudaFree(o->loss_rows); cudaFree(o->iota_rows);
+    free_side(o->pt); free_side(o->pd);
+    cudaFree(o->gbuf); cudaFree(o->dval_ord); cudaFree(o->row_batch); cudaFree(o->active); cudaFree(o->sort_temp);
+    cudaFree(o->rows_buf); cudaFree(o->row_off_buf); cudaFree(o->keep_buf); cudaFree(o->seed_dev);
+    cudaFree(o->loss_buf); cudaFree(o->partial); cudaFree(o->sc); cudaFree(o->step_dev);
+    if (o->ev) cudaEventDestroy(o->ev);
+    if (o->own_stream && o->st) cudaStreamDestroy(o->st);
+    return 0;
+}
+
+__global__ void iota32_kernel(int32_t* p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+}  // namespace dmt
+
+extern "C" {
+
+int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, int H2, const int32_t* d_indptr,
+                   const int32_t* d_indices, const float* d_val, int64_t d_nnz, const int32_t* t_indptr,
+                   const int32_t* t_indices, int64_t t_nnz, int batch_rows, int loss_kind, void* stream) {
+    DMT_REQUIRE(out && n_rows > 0 && n_enc > 0 && n_dec > 0 && batch_rows > 0, "dmt_org_create: bad sizes");
+    DMT_REQUIRE(H1 % 128 == 0 && H1 <= 512 && H2 > 0, "dmt_org_create: H1 must be 128/256/384/512");
+    DMT_REQUIRE(d_nnz >= 0 && t_nnz >= 0 && t_nnz < (1LL << 31) - 2 && d_nnz < (1LL << 31) - 2,
+                "dmt_org_create: nnz must fit int32");
+    int rc = dmt_check_device();
+    if (rc) return rc;
+    dmt_org* o = new (std::nothrow) dmt_org();
+    if (!o) return DMT_E_NOMEM;
+    *o = dmt_org{};
+    o->n_rows = n_rows; o->n_enc = n_enc; o->n_dec = n_dec; o->H1 = H1; o->H2 = H2;
+    o->batch_rows = batch_rows; o->loss_kind = loss_kind;
+    o->d_indptr = d_indptr; o->d_indices = d_indices; o->d_val = d_val; o->d_nnz = d_nnz;
+    o->t_indptr = t_indptr; o->t_indices = t_indices; o->t_val = nullptr; o->t_nnz = t_nnz;
+    if (stream) {
+        o->st = as_stream(stream);
+        o->own_stream = false;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&o->st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete o; set_error(cudaGetErrorString(e)); return (int)e; }
+        o->own_stream = true;
+    }
+    int64_t off = 0;
+    o->oW1 = off; off += (int64_t)n_enc * H1;
+    o->ob1 = off; off += H1;
+    o->oW2 = off; off += (int64_t)H2 * H1;
+    o->ob2 = off; off += H2;
+    o->oW3 = off; off += (int64_t)H1 * H2;
+    o->ob3 = off; off += H1;
+    o->oW4 = off; off += (int64_t)n_dec * H1;
+    o->ob4 = off; off += n_dec;
+    o->n_params = off;
+    o->act_rows = n_rows < 65536 ? n_rows : 65536;
+    if (o->act_rows < batch_rows) o->act_rows = batch_rows;
+    o->rows_cap = n_rows;
+    o->nb_cap = (n_rows + batch_rows - 1) / batch_rows + 1;
+#define A(expr) if ((rc = (expr))) { free_all(o); delete o; return rc; }
+    A(dalloc(&o->P, o->n_params)); A(dalloc(&o->G, o->n_params)); A(dalloc(&o->M, o->n_params));
+    A(dalloc(&o->V, o->n_params));
+    int64_t ar = o->act_rows;
+    A(dalloc(&o->a1, ar * H1)); A(dalloc(&o->a2, ar * H2)); A(dalloc(&o->c, ar * H2)); A(dalloc(&o->a3, ar * H1));
+    A(dalloc(&o->dz3, (int64_t)batch_rows * H1)); A(dalloc(&o->dz2, (int64_t)batch_rows * H2));
+    A(dalloc(&o->dz1, (int64_t)batch_rows * H1)); A(dalloc(&o->loss_rows, batch_rows));
+    A(dalloc(&o->iota_rows, n_rows));
+    A(alloc_side(o->pt, t_nnz, o->rows_cap, o->nb_cap)); A(alloc_side(o->pd, d_nnz, o->rows_cap, o->nb_cap));
+    A(dalloc(&o->gbuf, t_nnz)); A(dalloc(&o->dval_ord, d_nnz)); A(dalloc(&o->row_batch, o->rows_cap + 1));
+    A(dalloc(&o->active, o->nb_cap + 1));
+    o->sort_temp_bytes = sort_segments_temp_bytes(t_nnz > d_nnz ? t_nnz : d_nnz);
+    if (o->sort_temp_bytes < (1 << 20)) o->sort_temp_bytes = 1 << 20;
+    A(dalloc(reinterpret_cast<char**>(&o->sort_temp), o->sort_temp_bytes));
+    A(dalloc(&o->rows_buf, o->rows_cap)); A(dalloc(&o->row_off_buf, o->nb_cap + 1));
+    A(dalloc(&o->keep_buf, (int64_t)o->rows_cap * H2)); A(dalloc(&o->seed_dev, 1)); A(dalloc(&o->loss_buf, o->nb_cap));
+    A(dalloc(&o->partial, kNormBlocks)); A(dalloc(&o->sc, 1)); A(dalloc(&o->step_dev, 1));
+#undef A
+    {
+        cudaError_t e = cudaEventCreateWithFlags(&o->ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) { free_all(o); delete o; set_error(cudaGetErrorString(e)); return (int)e; }
+    }
+    iota32_kernel<<<(n_rows + 255) / 256, 256, 0, o->st>>>(o->iota_rows, n_rows);
+    cudaMemsetAsync(o->step_dev, 0, sizeof(int), o->st);
+    cudaMemsetAsync(o->M, 0, (size_t)o->n_params * 4, o->st);
+    cudaMemsetAsync(o->V, 0, (size_t)o->n_params * 4, o->st);
+    o->exec = nullptr;
+    o->g_nb = -1;
+    *out = o;
+    return 0;
+}
+
+int dmt_org_destroy(dmt_org_t* o) {
+    if (!o) return 0;
+    cudaStreamSynchronize(o->st);
+    free_all(o);
+    delete o;
+    return 0;
+}
+
+int64_t dmt_org_num_params(const dmt_org_t* o) { return o ? o->n_params : 0; }
+
+int dmt_org_set_params(dmt_org_t* o, const float* flat) {
+    DMT_REQUIRE(o && flat, "dmt_org_set_params: null");
+    DMT_CUDA(cudaMemcpyAsync(o->P, flat, (size_t)o->n_params * 4, cudaMemcpyDeviceToDevice, o->st));
+    DMT_CUDA(cudaMemsetAsync(o->M, 0, (size_t)o->n_params * 4, o->st));
+    DMT_CUDA(cudaMemsetAsync(o->V, 0, (size_t)o->n_params * 4, o->st));
+    DMT_CUDA(cudaMemsetAsync(o->step_dev, 0, sizeof(int), o->st));
+    return 0;
+}
+
+int dmt_org_get_params(const dmt_org_t* o, float* flat) {
+    DMT_REQUIRE(o && flat, "dmt_org_get_params: null");
+    DMT_CUDA(cudaMemcpyAsync(flat, o->P, (size_t)o->n_params * 4, cudaMemcpyDeviceToDevice, o->st));
+    return 0;
+}
+
+int dmt_org_set_target(dmt_org_t* o, const float* t_val) {
+    DMT_REQUIRE(o && t_val, "dmt_org_set_target: null");
+    if (o->t_val != t_val && o->exec) {  // the pointer is baked into the captured graph
+        cudaGraphExecDestroy(o->exec);
+        o->exec = nullptr;
+        o->g_nb = -1;
+    }
+    o->t_val = t_val;
+    return 0;
+}
+
+int dmt_org_train_epoch(dmt_org_t* o, const int32_t* rows, const int32_t* row_off, int n_rows_total, int n_batches,
+                        int64_t n_t_entries, int64_t n_d_entries, const uint8_t* keep, uint64_t seed, double lr,
+                        double beta1, double beta2, double eps, double weight_decay, float max_norm,
+                        float* epoch_loss) {
+    DMT_REQUIRE(o && rows && row_off, "dmt_org_train_epoch: null");
+    DMT_REQUIRE(o->t_val != nullptr, "dmt_org_train_epoch: call dmt_org_set_target first");
+    DMT_REQUIRE(n_batches >= 1 && n_batches <= o->nb_cap && n_rows_total >= 0 && n_rows_total <= o->rows_cap,
+                "dmt_org_train_epoch: too many rows or batches");
+    DMT_REQUIRE(n_t_entries <= o->pt.cap && n_d_entries <= o->pd.cap, "dmt_org_train_epoch: entry count over capacity");
+    DMT_REQUIRE((int64_t)n_batches * (o->n_dec > o->n_enc ? o->n_dec : o->n_enc) < (1LL << 32),
+                "dmt_org_train_epoch: batches x columns must fit 32-bit sort keys");
+    cudaStream_t st = o->st;
+    DMT_CUDA(cudaMemcpyAsync(o->rows_buf, rows, (size_t)n_rows_total * 4, cudaMemcpyDeviceToDevice, st));
+    DMT_CUDA(cudaMemcpyAsync(o->row_off_buf, row_off, (size_t)(n_batches + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    if (keep) DMT_CUDA(cudaMemcpyAsync(o->keep_buf, keep, (size_t)n_rows_total * o->H2, cudaMemcpyDeviceToDevice, st));
+    DMT_CUDA(cudaMemcpyAsync(o->seed_dev, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
+    int rc = build_plan(o, n_rows_total, n_batches, n_t_entries, n_d_entries);
+    if (rc) return rc;
+    AdamHyper hp{lr, beta1, beta2, eps, weight_decay, max_norm};
+    int use_keep = keep != nullptr;
+    if (!o->exec || o->g_nb != n_batches || o->g_keep != use_keep || !same_hp(hp, o->g_hp)) {
+        if (o->exec) { cudaGraphExecDestroy(o->exec); o->exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        DMT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int b = 0; b < n_batches && rc == 0; ++b) rc = enqueue_step(o, b, use_keep != 0, hp);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+        e = cudaGraphInstantiate(&o->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { o->exec = nullptr; set_error(cudaGetErrorString(e)); return (int)e; }
+        o->g_nb = n_batches; o->g_keep = use_keep; o->g_hp = hp;
+    }
+    DMT_CUDA(cudaGraphLaunch(o->exec, st));
+    if (epoch_loss)
+        DMT_CUDA(cudaMemcpyAsync(epoch_loss, o->loss_buf, (size_t)n_batches * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int dmt_org_predict(dmt_org_t* o, const int32_t* d_indptr, const int32_t* d_indices, const float* d_val,
+                    const int32_t* t_indptr, const int32_t* t_indices, int n_rows, float* pred) {
+    DMT_REQUIRE(o && pred && n_rows >= 0 && n_rows <= o->n_rows, "dmt_org_predict: bad argument");
+    cudaStream_t st = o->st;
+    const int H1 = o->H1, H2 = o->H2;
+    float *W1t = o->P + o->oW1, *b1 = o->P + o->ob1, *W2 = o->P + o->oW2, *b2 = o->P + o->ob2;
+    float *W3 = o->P + o->oW3, *b3 = o->P + o->ob3, *W4 = o->P + o->oW4, *b4 = o->P + o->ob4;
+    Dropout nodrop;
+    int rc;
+    for (int lo = 0; lo < n_rows; lo += o->act_rows) {
+        int hi = lo + o->act_rows < n_rows ? lo + o->act_rows : n_rows;
+        BatchRef br = batch_by_value(lo, hi);
+        int m = hi - lo;
+        if ((rc = launch_ae_encoder_fwd(o->iota_rows, d_indptr, d_indices, d_val, W1t, b1, H1, o->a1, m, br, st)))
+            return rc;
+        if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, nullptr, nodrop, m, H2, H1, 1, br, st))) return rc;
+        if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, m, H1, H2, 1, br, st))) return rc;
+        if ((rc = launch_ae_decoder_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1, o->loss_kind,
+                                        nullptr, nullptr, pred, nullptr, nullptr, nullptr, m, br, st)))
+            return rc;
+    }
+    return 0;
+}
+
+int dmt_org_sync(dmt_org_t* o) {
+    DMT_REQUIRE(o, "dmt_org_sync: null");
+    DMT_CUDA(cudaStreamSynchronize(o->st));
+    return 0;
+}
+
+void* dmt_org_stream(dmt_org_t* o) { return o ? (void*)o->st : nullptr; }
+
+int dmt_org_wait_stream(dmt_org_t* o, void* stream) {
+    DMT_REQUIRE(o, "dmt_org_wait_stream: null");
+    if (as_stream(stream) == o->st) return 0;
+    DMT_CUDA(cudaEventRecord(o->ev, as_stream(stream)));
+    DMT_CUDA(cudaStreamWaitEvent(o->st, o->ev, 0));
+    return 0;
+}
+
+int dmt_org_signal_stream(dmt_org_t* o, void* stream) {
+    DMT_REQUIRE(o, "dmt_org_signal_stream: null");
+    if (as_stream(stream) == o->st) return 0;
+    DMT_CUDA(cudaEventRecord(o->ev, o->st));
+    DMT_CUDA(cudaStreamWaitEvent(as_stream(stream), o->ev, 0));
+    return 0;
+}
+
+}  // extern "C"

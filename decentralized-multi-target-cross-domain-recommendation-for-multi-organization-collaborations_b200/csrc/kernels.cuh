@@ -1,0 +1,90 @@
+// Internal launch functions shared by the stateless C-ABI wrappers and the organization engine.
+#pragma once
+#include "common.cuh"
+
+namespace dmt {
+
+constexpr int kNormBlocks = kNumSMs * 2;
+
+struct AdamHyper {
+    double lr, beta1, beta2, eps, weight_decay;
+    float max_norm;  // <= 0: no clipping
+};
+struct AdamScalars {
+    float coef, step_size, bc2_sqrt;
+    int active;
+};
+
+// ---- optim.cu
+int launch_sqnorm_stage1(const float* g, int64_t n, float* partial, BatchRef br, cudaStream_t st);
+int launch_adam_prepare(const float* partial, int n_partial, const float* sqnorm_in, float* sqnorm_out,
+                        AdamScalars* sc, AdamHyper hp, int64_t step_by_value, int* step_dev, const float* loss_rows,
+                        const int32_t* n_targets_ptr, float* loss_out, BatchRef br, cudaStream_t st);
+int launch_adam(float* w, const float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
+                cudaStream_t st);
+
+// ---- dense.cu   (act: 0 none, 1 tanh, 2 relu)
+// Dropout source for the forward epilogue / backward mask: explicit keep bytes, or the counter-based generator.
+struct Dropout {
+    const uint8_t* keep = nullptr;       // 0/1 bytes, [rows x n]; nullptr -> counter-based generator
+    const uint64_t* seed_dev = nullptr;  // generator seed (device)
+    const int* step_dev = nullptr;       // device step counter mixed into the hash
+    const int32_t* row_base = nullptr;   // engine mode: mask row of in-batch row m is row_base[b] + m
+    int b = 0;
+    float scale = 1.f;  // 1/(1-p)
+    float p = 0.f;
+    int enabled = 0;
+};
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ float dropout_factor(const Dropout& d, int row, int col, int ld) {
+    if (!d.enabled) return 1.f;
+    int64_t r = (int64_t)row + (d.row_base ? d.row_base[d.b] : 0);
+    if (d.keep != nullptr) return d.keep[r * ld + col] ? d.scale : 0.f;
+    uint64_t seed = d.seed_dev ? *d.seed_dev : 0ull;
+    uint64_t t = d.step_dev ? (uint64_t)(*d.step_dev) : 0ull;
+    uint32_t h = mix32(seed ^ (t * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)r << 24) ^ (uint64_t)col);
+    return ((h >> 8) * (1.0f / 16777216.0f)) >= d.p ? d.scale : 0.f;
+}
+
+int launch_dense_fwd(const float* X, const float* W, const float* b, float* Y, float* Y_pre, Dropout drop, int m_max,
+                     int n, int k, int act, BatchRef br, cudaStream_t st);
+int launch_dense_bwd_x(const float* dY, const float* W, const float* A_prev, Dropout drop, float* dX, int m_max, int n,
+                       int k, int act_prev, BatchRef br, cudaStream_t st);
+int launch_dense_bwd_w(const float* dY, const float* X, float* dW, float* db, int m_max, int n, int k, BatchRef br,
+                       cudaStream_t st);
+int launch_colsum(const float* dY, int n, float* db, BatchRef br, cudaStream_t st);
+
+// ---- ae.cu
+int launch_ae_encoder_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* val,
+                          const float* W1t, const float* b1, int H, float* A1, int n_rows_max, BatchRef br,
+                          cudaStream_t st);
+// ent_off: when non-null, per-batch-row offsets into the batch-ordered entry space (gout is written there);
+// when null gout/pred are written at the CSR positions.
+int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
+                          const float* A3, const float* W4, const float* b4, int H, int loss_kind,
+                          const int32_t* n_targets, const int32_t* ent_off, float* pred, float* gout, float* dZ3,
+                          float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st);
+
+// ---- segments.cu
+struct SegRef {  // segments [seg_lo, seg_hi) either by value or from device batch_seg_off[b], [b+1]
+    const int32_t* batch_seg_off;
+    const int32_t* n_seg_dev;
+    int b;
+    int64_t lo, hi;
+    int32_t key_base_stride;  // column = seg_key - b * key_base_stride (0 for by-value use)
+};
+int launch_segment_reduce_rows(const int32_t* perm, const int32_t* seg_key, const int32_t* seg_off, SegRef sr,
+                               int64_t n_seg_max, const float* coef, const int32_t* src_row, const float* src,
+                               int width, float* grad, float* bias_grad, const int32_t* active, cudaStream_t st);
+int64_t sort_segments_temp_bytes(int64_t n);
+int sort_segments(const uint32_t* keys, int64_t n, int key_bits, int32_t* perm, int32_t* seg_key, int32_t* seg_off,
+                  int32_t* n_seg, void* temp, int64_t temp_bytes, cudaStream_t st);
+
+}  // namespace dmt

@@ -1,0 +1,335 @@
+// MTAL coordinator kernels: pseudo-residual, weighted combination of organization outputs, the fused
+// loss+gradient of the assisted-learning-rate / assistance-weight fit, and the round-0 mean predictor.
+// All are HBM-streaming passes: one coalesced read of each operand, one write, fp32.
+#include "common.cuh"
+
+namespace dmt {
+
+static thread_local char g_err[256] = "";
+void set_error(const char* msg) {
+    int i = 0;
+    for (; msg[i] && i < 255; ++i) g_err[i] = msg[i];
+    g_err[i] = 0;
+}
+
+// ---------------------------------------------------------------- residual (reference src/assist.py:45-58)
+__global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__ F, const float* __restrict__ y,
+                                                       float* __restrict__ r, int64_t n, int kind, float clamp) {
+    int64_t n4 = n >> 2;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 f = ld4(F + 4 * i), t = ld4(y + 4 * i), o;
+        float* fo = &o.x;
+        const float* ff = &f.x;
+        const float* tt = &t.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float g = loss_grad(kind, ff[k], tt[k]);
+            if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
+            fo[k] = -g;
+        }
+        st4(r + 4 * i, o);
+    }
+    // tail
+    for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float g = loss_grad(kind, F[i], y[i]);
+        if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
+        r[i] = -g;
+    }
+}
+
+// ---------------------------------------------------------------- combine (reference src/assist.py:131-176)
+// One pass over the global CSR for all owners. S (K x K softmax rows) is staged in shared memory.
+template <int KMAX>
+__global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ F_old, const float* __restrict__ O,
+                                                      const int32_t* __restrict__ col,
+                                                      const int32_t* __restrict__ owner,
+                                                      const float* __restrict__ rate_col, const float* __restrict__ S,
+                                                      const int64_t* __restrict__ match_end, float* __restrict__ F_new,
+                                                      int64_t nnz, int K) {
+    extern __shared__ float sS[];  // K*K
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) sS[i] = S[i];
+    __syncthreads();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
+        int c = col[p];
+        int ow = owner[c];
+        const float* s = sS + ow * K;
+        float q = 0.f;
+        if (match_end == nullptr || p < match_end[ow]) {
+#pragma unroll 4
+            for (int j = 0; j < K; ++j) q += O[(int64_t)j * nnz + p] * s[j];
+        } else {
+            // unmatched entry: the owner's own output fills every slot (reference src/assist.py:98-103)
+            float own = O[(int64_t)ow * nnz + p];
+            for (int j = 0; j < K; ++j) q += own * s[j];
+        }
+        F_new[p] = F_old[p] + rate_col[c] * q;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_view_kernel(const float* __restrict__ F_old, const float* __restrict__ y,
+                                                          const float* __restrict__ O, const int32_t* __restrict__ pos,
+                                                          const int32_t* __restrict__ rank, int64_t nnz, int64_t n,
+                                                          int K, int owner, int64_t n_match, float* __restrict__ h,
+                                                          float* __restrict__ t, float* __restrict__ V) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        int64_t p = pos[e];
+        h[e] = F_old[p];
+        t[e] = y[p];
+        bool matched = rank[e] < n_match;
+        float own = O[(int64_t)owner * nnz + p];
+        for (int j = 0; j < K; ++j) V[(int64_t)j * n + e] = matched ? O[(int64_t)j * nnz + p] : own;
+    }
+}
+
+// ---------------------------------------------------------------- fused loss + grad of models.Assist
+// scratch layout: [0] loss partials (NB), then d_s partials (NB x K). One warp per owned column (segment) so the
+// per-column rate gradient is a warp-segmented reduction without atomics; the K-vector d_s is reduced per block
+// and finished by a second tiny kernel (deterministic two-stage).
+constexpr int kAssistBlocks = kNumSMs * 2;
+constexpr int kAssistKMax = 64;
+
+__global__ void __launch_bounds__(256) assist_loss_grad_kernel(const float* __restrict__ h, const float* __restrict__ t,
+                                                               const float* __restrict__ V,
+                                                               const int32_t* __restrict__ seg_off,
+                                                               const float* __restrict__ rate,
+                                                               const float* __restrict__ w, int64_t n, int n_rate, int K,
+                                                               int kind, float* __restrict__ d_rate,
+                                                               float* __restrict__ scratch) {
+    __shared__ float s_soft[kAssistKMax];
+    __shared__ float s_ds[8][kAssistKMax];
+    __shared__ float s_loss[8];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, w[j]);
+        float z = 0.f;
+        for (int j = 0; j < K; ++j) {
+            s_soft[j] = expf(w[j] - mx);
+            z += s_soft[j];
+        }
+        for (int j = 0; j < K; ++j) s_soft[j] /= z;
+    }
+    for (int j = lane; j < K; j += 32) s_ds[wid][j] = 0.f;
+    __syncthreads();
+    float inv_n = 1.f / (float)n;
+    float loss_acc = 0.f;
+    int warps_total = gridDim.x * 8;
+    for (int c = blockIdx.x * 8 + wid; c < n_rate; c += warps_total) {
+        int e0 = seg_off[c], e1 = seg_off[c + 1];
+        float eta = rate[c];
+        float dr = 0.f;
+        for (int eb = e0; eb < e1; eb += 32) {  // warp-uniform trip count: the shuffles below need all lanes
+            int e = eb + lane;
+            bool ok = e < e1;
+            float q = 0.f, de = 0.f;
+            if (ok) {
+                for (int j = 0; j < K; ++j) q += V[(int64_t)j * n + e] * s_soft[j];
+                float o = h[e] + eta * q;
+                float y = t[e];
+                loss_acc += loss_value(kind, o, y);
+                float delta = loss_grad(kind, o, y) * inv_n;
+                dr += delta * q;
+                de = delta * eta;
+            }
+            for (int j = 0; j < K; ++j) {
+                float v = ok ? de * V[(int64_t)j * n + e] : 0.f;
+                v = warp_sum(v);
+                if (lane == 0) s_ds[wid][j] += v;
+            }
+        }
+        dr = warp_sum(dr);
+        if (lane == 0) d_rate[c] = dr;
+    }
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0) s_loss[wid] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float l = 0.f;
+        for (int i = 0; i < 8; ++i) l += s_loss[i];
+        scratch[blockIdx.x] = l * inv_n;
+    }
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        float v = 0.f;
+        for (int i = 0; i < 8; ++i) v += s_ds[i][j];
+        scratch[gridDim.x + (int64_t)blockIdx.x * K + j] = v;
+    }
+}
+
+__global__ void assist_finish_kernel(const float* __restrict__ scratch, const float* __restrict__ w, int K, int nb,
+                                     float* __restrict__ out_loss, float* __restrict__ d_w) {
+    __shared__ float sh[32];
+    __shared__ float s_soft[kAssistKMax];
+    __shared__ float s_ds[kAssistKMax];
+    float l = 0.f;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) l += scratch[i];
+    l = block_sum(l, sh);
+    if (threadIdx.x == 0) out_loss[0] = l;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        float v = 0.f;
+        for (int i = 0; i < nb; ++i) v += scratch[nb + (int64_t)i * K + j];
+        s_ds[j] = v;
+    }
+    if (threadIdx.x == 0) {
+        float mx = -INFINITY;
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, w[j]);
+        float z = 0.f;
+        for (int j = 0; j < K; ++j) {
+            s_soft[j] = expf(w[j] - mx);
+            z += s_soft[j];
+        }
+        for (int j = 0; j < K; ++j) s_soft[j] /= z;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // d/dw of softmax: dw_j = s_j (ds_j - sum_k s_k ds_k)
+        float dot = 0.f;
+        for (int j = 0; j < K; ++j) dot += s_soft[j] * s_ds[j];
+        for (int j = 0; j < K; ++j) d_w[j] = s_soft[j] * (s_ds[j] - dot);
+    }
+}
+
+// ---------------------------------------------------------------- models.Base (reference src/models/base.py:22-60)
+__global__ void __launch_bounds__(256) base_fit_kernel(const int32_t* __restrict__ idx, const float* __restrict__ rating,
+                                                       int64_t n, float* base, float* count) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // ratings are small integers ({1..5} or {0,1}): fp32 sums are exact, so the atomic order cannot matter
+        atomicAdd(base + idx[i], rating[i]);
+        atomicAdd(count + idx[i], 1.f);
+    }
+}
+
+// mean of the seen means -> scratch[0]; single block (n_cols is the number of columns of one organization)
+__global__ void base_fill_kernel(const float* __restrict__ base, const float* __restrict__ count, int n_cols,
+                                 float* scratch) {
+    __shared__ float sh[32];
+    float s = 0.f, c = 0.f;
+    for (int i = threadIdx.x; i < n_cols; i += blockDim.x) {
+        if (count[i] != 0.f) {
+            s += base[i] / count[i];
+            c += 1.f;
+        }
+    }
+    s = block_sum(s, sh);
+    c = block_sum(c, sh);
+    if (threadIdx.x == 0) scratch[0] = s / c;
+}
+
+__global__ void __launch_bounds__(256) base_predict_kernel(const float* __restrict__ base,
+                                                           const float* __restrict__ count,
+                                                           const int32_t* __restrict__ tidx, int64_t n, int implicit,
+                                                           float implicit_count, const float* __restrict__ fill,
+                                                           float* __restrict__ out) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int c = tidx[i];
+        if (implicit) {
+            out[i] = base[c] / implicit_count;
+        } else {
+            float cnt = count[c];
+            out[i] = (cnt == 0.f) ? fill[0] : base[c] / (cnt + 1e-10f);
+        }
+    }
+}
+
+static inline int stream_grid(int64_t n, int per_thread = 4) {
+    int64_t blocks = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+    int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace dmt
+
+using namespace dmt;
+
+extern "C" {
+
+const char* dmt_last_error(void) { return g_err; }
+int dmt_version(void) { return 100; }
+
+int dmt_check_device(void) {
+    int dev = 0;
+    DMT_CUDA(cudaGetDevice(&dev));
+    int major = 0;
+    DMT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        set_error("libdmt_b200 is built for sm_100a only");
+        return DMT_E_ARCH;
+    }
+    return 0;
+}
+
+int dmt_residual(const float* F, const float* y, float* r, int64_t n, int loss_kind, float clamp, void* stream) {
+    DMT_REQUIRE(n >= 0 && (loss_kind == DMT_LOSS_MSE || loss_kind == DMT_LOSS_BCE), "dmt_residual: bad argument");
+    if (n == 0) return 0;
+    residual_kernel<<<stream_grid(n, 8), 256, 0, as_stream(stream)>>>(F, y, r, n, loss_kind, clamp);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int dmt_assist_combine(const float* F_old, const float* O, const int32_t* col, const int32_t* owner,
+                       const float* rate_col, const float* S, const int64_t* match_end, float* F_new, int64_t nnz,
+                       int K, void* stream) {
+    DMT_REQUIRE(nnz >= 0 && K >= 1 && K <= 128, "dmt_assist_combine: need 1 <= K <= 128");
+    if (nnz == 0) return 0;
+    combine_kernel<128><<<stream_grid(nnz, 2), 256, K * K * sizeof(float), as_stream(stream)>>>(
+        F_old, O, col, owner, rate_col, S, match_end, F_new, nnz, K);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int dmt_assist_gather_view(const float* F_old, const float* y, const float* O, const int32_t* pos,
+                           const int32_t* rank, int64_t nnz, int64_t n, int K, int owner, int64_t n_match, float* h,
+                           float* t, float* V, void* stream) {
+    DMT_REQUIRE(n >= 0 && K >= 1 && owner >= 0 && owner < K, "dmt_assist_gather_view: bad argument");
+    if (n == 0) return 0;
+    gather_view_kernel<<<stream_grid(n, 1), 256, 0, as_stream(stream)>>>(F_old, y, O, pos, rank, nnz, n, K, owner,
+                                                                         n_match, h, t, V);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t dmt_assist_scratch_floats(int K) { return (int64_t)kAssistBlocks * (1 + K); }
+
+int dmt_assist_loss_grad(const float* h, const float* t, const float* V, const int32_t* seg_off, const float* rate,
+                         const float* w, int64_t n, int n_rate, int K, int loss_kind, float* out_loss, float* d_rate,
+                         float* d_w, float* scratch, void* stream) {
+    DMT_REQUIRE(n > 0 && n_rate > 0 && K >= 1 && K <= kAssistKMax, "dmt_assist_loss_grad: need n>0 and 1 <= K <= 64");
+    int nb = (n_rate + 7) / 8;
+    if (nb > kAssistBlocks) nb = kAssistBlocks;
+    assist_loss_grad_kernel<<<nb, 256, 0, as_stream(stream)>>>(h, t, V, seg_off, rate, w, n, n_rate, K, loss_kind,
+                                                              d_rate, scratch);
+    DMT_LAUNCH_CHECK();
+    assist_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(scratch, w, K, nb, out_loss, d_w);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int dmt_base_fit(const int32_t* idx, const float* rating, int64_t n, float* base, float* count, void* stream) {
+    DMT_REQUIRE(n >= 0, "dmt_base_fit: bad n");
+    if (n == 0) return 0;
+    base_fit_kernel<<<stream_grid(n, 2), 256, 0, as_stream(stream)>>>(idx, rating, n, base, count);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int dmt_base_predict(const float* base, const float* count, int32_t n_cols, const int32_t* target_idx, int64_t n,
+                     int implicit, float implicit_count, float* out, float* scratch, void* stream) {
+    DMT_REQUIRE(n >= 0 && n_cols > 0, "dmt_base_predict: bad argument");
+    if (!implicit) {
+        base_fill_kernel<<<1, 1024, 0, as_stream(stream)>>>(base, count, n_cols, scratch);
+        DMT_LAUNCH_CHECK();
+    }
+    if (n == 0) return 0;
+    base_predict_kernel<<<stream_grid(n, 2), 256, 0, as_stream(stream)>>>(base, count, target_idx, n, implicit,
+                                                                          implicit_count, scratch, out);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

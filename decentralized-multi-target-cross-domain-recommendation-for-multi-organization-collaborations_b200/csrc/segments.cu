@@ -1,0 +1,192 @@
+// Sort-by-index and warp-segmented reduction: the dense-gradient form of autograd's embedding / gather backward
+// without contended atomics (reference call sites: nn.Embedding at src/models/mf.py:37,44; weight gathers at
+// src/models/ae.py:102,135-136; torch.sort/unique_consecutive at ae.py:103-104,137-139).
+//   1. stable LSD radix sort of (key, position) pairs (CUB device primitive) -> perm
+//   2. run-length encode the sorted keys -> unique keys, counts -> exclusive scan -> segment offsets
+//   3. one warp per segment accumulates coef * source-row in registers and writes the gradient row once.
+// Deterministic: the order inside a segment is the stable (position) order.
+#include <cub/cub.cuh>
+
+#include "kernels.cuh"
+
+namespace dmt {
+
+__global__ void iota_kernel(int32_t* p, int64_t n) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = (int32_t)i;
+}
+
+// temp layout: [keys_out n u32][vals_in n i32][counts n i32][cub temp ...]
+static size_t cub_temp_bytes(int64_t n) {
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)n, 0, 32);
+    cub::DeviceRunLengthEncode::Encode(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,
+                                       (int32_t*)nullptr, (int)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n + 1);
+    size_t m = a > b ? a : b;
+    return m > c ? m : c;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int64_t sort_segments_temp_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return (int64_t)(3 * align256((size_t)(n + 1) * 4) + align256(cub_temp_bytes(n)) + 256);
+}
+
+__global__ void close_offsets_kernel(int32_t* seg_off, const int32_t* n_seg, int32_t n) {
+    // ExclusiveSum over counts[0..n_seg) padded with zeros leaves seg_off[n_seg] = n already; this only pins the
+    // terminator in case the padding was not zero.
+    if (threadIdx.x == 0 && blockIdx.x == 0) seg_off[n_seg[0]] = n;
+}
+
+int sort_segments(const uint32_t* keys, int64_t n, int key_bits, int32_t* perm, int32_t* seg_key, int32_t* seg_off,
+                  int32_t* n_seg, void* temp, int64_t temp_bytes, cudaStream_t st) {
+    if (n <= 0) {
+        DMT_CUDA(cudaMemsetAsync(n_seg, 0, sizeof(int32_t), st));
+        DMT_CUDA(cudaMemsetAsync(seg_off, 0, sizeof(int32_t), st));
+        return 0;
+    }
+    if (temp_bytes < sort_segments_temp_bytes(n)) {
+        set_error("sort_segments: temp buffer too small");
+        return DMT_E_ARG;
+    }
+    char* base = reinterpret_cast<char*>(temp);
+    size_t slot = align256((size_t)(n + 1) * 4);
+    uint32_t* keys_out = reinterpret_cast<uint32_t*>(base);
+    int32_t* vals_in = reinterpret_cast<int32_t*>(base + slot);
+    int32_t* counts = reinterpret_cast<int32_t*>(base + 2 * slot);
+    void* cub_temp = base + 3 * slot;
+    size_t cub_bytes = cub_temp_bytes(n);
+    int blocks = (int)((n + 1023) / 1024);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    iota_kernel<<<blocks, 256, 0, st>>>(vals_in, n);
+    DMT_LAUNCH_CHECK();
+    if (key_bits < 1) key_bits = 1;
+    if (key_bits > 32) key_bits = 32;
+    DMT_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys, keys_out, vals_in, perm, (int)n, 0, key_bits,
+                                             st));
+    DMT_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, st));
+    DMT_CUDA(cub::DeviceRunLengthEncode::Encode(cub_temp, cub_bytes, keys_out, reinterpret_cast<uint32_t*>(seg_key),
+                                                counts, n_seg, (int)n, st));
+    DMT_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, counts, seg_off, (int)n + 1, st));
+    close_offsets_kernel<<<1, 32, 0, st>>>(seg_off, n_seg, (int32_t)n);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+// One warp per segment; VEC float4 slices per lane (width = VEC*128).
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_reduce_rows_kernel(const int32_t* __restrict__ perm,
+                                                                  const int32_t* __restrict__ seg_key,
+                                                                  const int32_t* __restrict__ seg_off, SegRef sr,
+                                                                  const float* __restrict__ coef,
+                                                                  const int32_t* __restrict__ src_row,
+                                                                  const float* __restrict__ src,
+                                                                  float* __restrict__ grad,
+                                                                  float* __restrict__ bias_grad,
+                                                                  const int32_t* __restrict__ active) {
+    constexpr int W = VEC * 128;
+    int64_t s_lo = sr.lo, s_hi = sr.hi;
+    uint32_t key_base = 0;
+    if (sr.batch_seg_off != nullptr) {
+        if (active != nullptr && active[sr.b] == 0) return;
+        s_lo = sr.batch_seg_off[sr.b];
+        s_hi = sr.batch_seg_off[sr.b + 1];
+        key_base = (uint32_t)sr.b * (uint32_t)sr.key_base_stride;
+    } else if (sr.n_seg_dev != nullptr) {
+        s_hi = sr.n_seg_dev[0];
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t s = s_lo + warp; s < s_hi; s += n_warps) {
+        const int e0 = seg_off[s], e1 = seg_off[s + 1];
+        const int row_out = (int)((uint32_t)seg_key[s] - key_base);
+        float4 acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bsum = 0.f;
+        for (int eb = e0; eb < e1; eb += 32) {
+            int e = eb + lane;
+            float c_l = 0.f;
+            int r_l = 0;
+            if (e < e1) {
+                int id = perm[e];
+                c_l = coef[id];
+                r_l = src_row[id];
+            }
+            bsum += c_l;
+            int cnt = min(32, e1 - eb);
+            for (int i = 0; i < cnt; ++i) {
+                float c = __shfl_sync(0xffffffffu, c_l, i);
+                int r = __shfl_sync(0xffffffffu, r_l, i);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float4 x = ld4(src + (int64_t)r * W + v * 128 + lane * 4);
+                    acc[v].x = fmaf(c, x.x, acc[v].x);
+                    acc[v].y = fmaf(c, x.y, acc[v].y);
+                    acc[v].z = fmaf(c, x.z, acc[v].z);
+                    acc[v].w = fmaf(c, x.w, acc[v].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) st4(grad + (int64_t)row_out * W + v * 128 + lane * 4, acc[v]);
+        if (bias_grad != nullptr) {
+            bsum = warp_sum(bsum);
+            if (lane == 0) bias_grad[row_out] = bsum;
+        }
+    }
+}
+
+int launch_segment_reduce_rows(const int32_t* perm, const int32_t* seg_key, const int32_t* seg_off, SegRef sr,
+                               int64_t n_seg_max, const float* coef, const int32_t* src_row, const float* src,
+                               int width, float* grad, float* bias_grad, const int32_t* active, cudaStream_t st) {
+    if (n_seg_max <= 0) return 0;
+    int64_t blocks = (n_seg_max + 7) / 8;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+#define DMT_SEG(V)                                                                                            \
+    segment_reduce_rows_kernel<V><<<(int)blocks, 256, 0, st>>>(perm, seg_key, seg_off, sr, coef, src_row, src, \
+                                                              grad, bias_grad, active)
+    if (width == 128) DMT_SEG(1);
+    else if (width == 256) DMT_SEG(2);
+    else if (width == 384) DMT_SEG(3);
+    else if (width == 512) DMT_SEG(4);
+    else {
+        set_error("segment_reduce_rows: width must be 128, 256, 384 or 512");
+        return DMT_E_ARG;
+    }
+#undef DMT_SEG
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dmt
+
+using namespace dmt;
+
+extern "C" {
+
+int64_t dmt_sort_segments_temp_bytes(int64_t n) { return sort_segments_temp_bytes(n); }
+
+int dmt_sort_segments(const int32_t* keys, int64_t n, int32_t key_bound, int32_t* perm, int32_t* seg_key,
+                      int32_t* seg_off, int32_t* n_seg, void* temp, int64_t temp_bytes, void* stream) {
+    DMT_REQUIRE(n >= 0 && n < (1LL << 31) - 1 && key_bound > 0, "dmt_sort_segments: bad argument");
+    int bits = 1;
+    while (bits < 32 && (1LL << bits) < (int64_t)key_bound) ++bits;
+    return sort_segments(reinterpret_cast<const uint32_t*>(keys), n, bits, perm, seg_key, seg_off, n_seg, temp,
+                         temp_bytes, as_stream(stream));
+}
+
+int dmt_segment_reduce_rows(const int32_t* perm, const int32_t* seg_key, const int32_t* seg_off, const int32_t* n_seg,
+                            int64_t n_seg_max, const float* coef, const int32_t* src_row, const float* src, int width,
+                            float* grad, float* bias_grad, void* stream) {
+    DMT_REQUIRE(n_seg_max >= 0, "dmt_segment_reduce_rows: bad argument");
+    SegRef sr{nullptr, n_seg, 0, 0, n_seg_max, 0};
+    return launch_segment_reduce_rows(perm, seg_key, seg_off, sr, n_seg_max, coef, src_row, src, width, grad,
+                                      bias_grad, nullptr, as_stream(stream));
+}
+
+}  // extern "C"

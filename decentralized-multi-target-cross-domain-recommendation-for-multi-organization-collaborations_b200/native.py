@@ -1,0 +1,381 @@
+"""ctypes binding of libdmt_b200.so — the C-ABI declared in include/dmt_b200.h.
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised. torch is used
+only as the owner of device memory and streams (``tensor.data_ptr()``, ``current_stream().cuda_stream``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+_LIB = None
+
+c_i32p = C.c_void_p  # device pointers are passed as opaque addresses
+c_f32p = C.c_void_p
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Load the shared library (building it in-tree with nvcc when absent). Raises if it cannot be had."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise NativeError("libdmt_b200.so is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _build.build_native()
+    lib = C.CDLL(path)
+    _declare(lib)
+    _LIB = lib
+    return lib
+
+
+def _declare(lib):
+    P, I, L, F, D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    lib.dmt_last_error.restype = C.c_char_p
+    lib.dmt_last_error.argtypes = []
+    sig = {
+        "dmt_version": (I, []),
+        "dmt_check_device": (I, []),
+        "dmt_residual": (I, [P, P, P, L, I, F, P]),
+        "dmt_assist_combine": (I, [P, P, P, P, P, P, P, P, L, I, P]),
+        "dmt_assist_gather_view": (I, [P, P, P, P, P, L, L, I, I, L, P, P, P, P]),
+        "dmt_assist_scratch_floats": (L, [I]),
+        "dmt_assist_loss_grad": (I, [P, P, P, P, P, P, L, I, I, I, P, P, P, P, P]),
+        "dmt_base_fit": (I, [P, P, L, P, P, P]),
+        "dmt_base_predict": (I, [P, P, C.c_int32, P, L, I, F, P, P, P]),
+        "dmt_sort_segments_temp_bytes": (L, [L]),
+        "dmt_sort_segments": (I, [P, L, C.c_int32, P, P, P, P, P, L, P]),
+        "dmt_segment_reduce_rows": (I, [P, P, P, P, L, P, P, P, I, P, P, P]),
+        "dmt_sqnorm_scratch_floats": (L, []),
+        "dmt_sqnorm": (I, [P, L, P, P, P]),
+        "dmt_adam_clip_step": (I, [P, P, P, P, L, P, F, D, D, D, D, D, L, P, P]),
+        "dmt_mf_scratch_floats": (L, []),
+        "dmt_mf_fwd": (I, [P, P, P, L, P, P, P, P, P, P, P, I, I, P, P, P, P, P]),
+        "dmt_mf_bwd_table": (I, [P, P, P, P, I, P, F, P, P, P, P, L, P, P, P]),
+        "dmt_mf_bwd_side": (I, [P, L, P, P, I, P, F, P, P]),
+        "dmt_dense_fwd": (I, [P, P, P, P, P, P, F, I, I, I, I, P]),
+        "dmt_dense_bwd_x": (I, [P, P, P, P, F, P, I, I, I, I, P]),
+        "dmt_dense_bwd_w": (I, [P, P, P, P, I, I, I, P]),
+        "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
+        "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
+        "dmt_org_create": (I, [C.POINTER(P), I, I, I, I, I, P, P, P, L, P, P, L, I, I, P]),
+        "dmt_org_destroy": (I, [P]),
+        "dmt_org_num_params": (L, [P]),
+        "dmt_org_set_params": (I, [P, P]),
+        "dmt_org_get_params": (I, [P, P]),
+        "dmt_org_set_target": (I, [P, P]),
+        "dmt_org_train_epoch": (I, [P, P, P, I, I, L, L, P, C.c_uint64, D, D, D, D, D, F, P]),
+        "dmt_org_predict": (I, [P, P, P, P, P, P, I, P]),
+        "dmt_org_sync": (I, [P]),
+        "dmt_org_stream": (P, [P]),
+        "dmt_org_wait_stream": (I, [P, P]),
+        "dmt_org_signal_stream": (I, [P, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+
+
+EXPORTS = None  # filled lazily for the symbol test
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().dmt_last_error().decode() if _LIB is not None else ""
+        raise NativeError("{} failed (code {}): {}".format(what, rc, msg))
+
+
+def ptr(t):
+    """Device address of a tensor (None -> NULL). The tensor must be CUDA and contiguous."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("dmtcdr_b200 kernels need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise NativeError("non-contiguous tensor passed to a native kernel")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+def f32(t):
+    return t.to(torch.float32).contiguous()
+
+
+LOSS_KIND = {"explicit": 0, "implicit": 1}
+
+# ------------------------------------------------------------------------------------------ thin wrappers
+
+
+def residual(F, y, loss_kind, clamp=0.0, out=None):
+    lib = load()
+    out = torch.empty_like(F) if out is None else out
+    check(lib.dmt_residual(ptr(F), ptr(y), ptr(out), F.numel(), loss_kind, float(clamp), stream()), "dmt_residual")
+    return out
+
+
+def assist_combine(F_old, O, col, owner, rate_col, S, match_end=None, out=None):
+    lib = load()
+    K, nnz = O.shape
+    out = torch.empty_like(F_old) if out is None else out
+    check(lib.dmt_assist_combine(ptr(F_old), ptr(O), ptr(col), ptr(owner), ptr(rate_col), ptr(S), ptr(match_end),
+                                 ptr(out), nnz, K, stream()), "dmt_assist_combine")
+    return out
+
+
+def assist_gather_view(F_old, y, O, pos, rank, owner, n_match):
+    lib = load()
+    K, nnz = O.shape
+    n = pos.numel()
+    h = torch.empty(n, device=O.device, dtype=torch.float32)
+    t = torch.empty_like(h)
+    V = torch.empty(K, n, device=O.device, dtype=torch.float32)
+    check(lib.dmt_assist_gather_view(ptr(F_old), ptr(y), ptr(O), ptr(pos), ptr(rank), nnz, n, K, owner, n_match,
+                                     ptr(h), ptr(t), ptr(V), stream()), "dmt_assist_gather_view")
+    return h, t, V
+
+
+def assist_loss_grad(h, t, V, seg_off, rate, w, loss_kind, scratch=None):
+    lib = load()
+    K, n = V.shape
+    n_rate = rate.numel()
+    if scratch is None:
+        scratch = torch.empty(lib.dmt_assist_scratch_floats(K), device=V.device, dtype=torch.float32)
+    out = torch.empty(1 + n_rate + K, device=V.device, dtype=torch.float32)
+    d_rate = out[1:1 + n_rate]
+    d_w = out[1 + n_rate:]
+    d_rate.zero_()
+    check(lib.dmt_assist_loss_grad(ptr(h), ptr(t), ptr(V), ptr(seg_off), ptr(rate), ptr(w), n, n_rate, K, loss_kind,
+                                   ptr(out), d_rate.data_ptr(), d_w.data_ptr(), ptr(scratch), stream()),
+          "dmt_assist_loss_grad")
+    return out  # [loss, d_rate..., d_w...]
+
+
+def base_fit(idx, rating, base, count):
+    check(load().dmt_base_fit(ptr(idx), ptr(rating), idx.numel(), ptr(base), ptr(count), stream()), "dmt_base_fit")
+
+
+def base_predict(base, count, target_idx, implicit, implicit_count=0.0):
+    out = torch.empty(target_idx.numel(), device=base.device, dtype=torch.float32)
+    scratch = torch.empty(2, device=base.device, dtype=torch.float32)
+    check(load().dmt_base_predict(ptr(base), ptr(count), base.numel(), ptr(target_idx), target_idx.numel(),
+                                  int(implicit), float(implicit_count), ptr(out), ptr(scratch), stream()),
+          "dmt_base_predict")
+    return out
+
+
+def sort_segments(keys, key_bound):
+    """-> perm, seg_key, seg_off, n_seg (device int32 tensors; seg_* sized for the worst case)."""
+    lib = load()
+    n = keys.numel()
+    dev = keys.device
+    perm = torch.empty(max(n, 1), device=dev, dtype=torch.int32)
+    seg_key = torch.empty(max(n, 1), device=dev, dtype=torch.int32)
+    seg_off = torch.zeros(n + 2, device=dev, dtype=torch.int32)
+    n_seg = torch.zeros(1, device=dev, dtype=torch.int32)
+    nbytes = lib.dmt_sort_segments_temp_bytes(n)
+    temp = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    check(lib.dmt_sort_segments(ptr(keys), n, int(key_bound), ptr(perm), ptr(seg_key), ptr(seg_off), ptr(n_seg),
+                                ptr(temp), nbytes, stream()), "dmt_sort_segments")
+    return perm, seg_key, seg_off, n_seg
+
+
+def segment_reduce_rows(perm, seg_key, seg_off, n_seg, n_seg_max, coef, src_row, src, grad, bias_grad=None):
+    width = src.shape[-1]
+    check(load().dmt_segment_reduce_rows(ptr(perm), ptr(seg_key), ptr(seg_off), ptr(n_seg), n_seg_max, ptr(coef),
+                                         ptr(src_row), ptr(src), width, ptr(grad), ptr(bias_grad), stream()),
+          "dmt_segment_reduce_rows")
+
+
+def sqnorm(g):
+    lib = load()
+    out = torch.empty(1, device=g.device, dtype=torch.float32)
+    scratch = torch.empty(lib.dmt_sqnorm_scratch_floats(), device=g.device, dtype=torch.float32)
+    check(lib.dmt_sqnorm(ptr(g), g.numel(), ptr(out), ptr(scratch), stream()), "dmt_sqnorm")
+    return out
+
+
+def adam_clip_step(w, g, m, v, step, sqnorm_t=None, max_norm=1.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                   weight_decay=5e-4):
+    scratch = torch.empty(8, device=w.device, dtype=torch.float32)
+    check(load().dmt_adam_clip_step(ptr(w), ptr(g), ptr(m), ptr(v), w.numel(), ptr(sqnorm_t), float(max_norm),
+                                    float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                    int(step), ptr(scratch), stream()), "dmt_adam_clip_step")
+
+
+def mf_fwd(user, item, rating, Wu, Wi, bu, bi, bias, loss_kind, pu=None, pi=None, want_grad=True):
+    lib = load()
+    n = user.numel()
+    dev = Wu.device
+    pred = torch.empty(n, device=dev, dtype=torch.float32)
+    dpred = torch.empty(n, device=dev, dtype=torch.float32) if want_grad else None
+    sums = torch.empty(2, device=dev, dtype=torch.float32)
+    scratch = torch.empty(lib.dmt_mf_scratch_floats(), device=dev, dtype=torch.float32)
+    check(lib.dmt_mf_fwd(ptr(user), ptr(item), ptr(rating), n, ptr(Wu), ptr(Wi), ptr(bu), ptr(bi), ptr(bias), ptr(pu),
+                         ptr(pi), Wu.shape[1], loss_kind, ptr(pred), ptr(dpred), ptr(sums), ptr(scratch), stream()),
+          "dmt_mf_fwd")
+    return pred, dpred, sums
+
+
+def mf_bwd_table(other, W_other, b_other, p_side, dpred, scale, seg, n_rows):
+    """Dense grads (dW [n_rows x H], db [n_rows]) of the table whose sorted segments are ``seg``."""
+    perm, seg_key, seg_off, n_seg = seg
+    H = W_other.shape[1]
+    dW = torch.zeros(n_rows, H, device=W_other.device, dtype=torch.float32)
+    db = torch.zeros(n_rows, device=W_other.device, dtype=torch.float32)
+    check(load().dmt_mf_bwd_table(ptr(other), ptr(W_other), ptr(b_other), ptr(p_side), H, ptr(dpred), float(scale),
+                                  ptr(perm), ptr(seg_key), ptr(seg_off), ptr(n_seg), min(n_rows, other.numel()),
+                                  ptr(dW), ptr(db), stream()), "dmt_mf_bwd_table")
+    return dW, db
+
+
+def mf_bwd_side(idx, W, b, dpred, scale):
+    H = W.shape[1]
+    d_p = torch.empty(idx.numel(), H, device=W.device, dtype=torch.float32)
+    check(load().dmt_mf_bwd_side(ptr(idx), idx.numel(), ptr(W), ptr(b), H, ptr(dpred), float(scale), ptr(d_p),
+                                 stream()), "dmt_mf_bwd_side")
+    return d_p
+
+
+def dense_fwd(X, W, b, act, keep=None, keep_scale=1.0):
+    m, k = X.shape
+    n = W.shape[0]
+    Y = torch.empty(m, n, device=X.device, dtype=torch.float32)
+    Y_pre = torch.empty_like(Y) if keep is not None else None
+    check(load().dmt_dense_fwd(ptr(X), ptr(W), ptr(b), ptr(Y), ptr(Y_pre), ptr(keep), float(keep_scale), m, n, k, act,
+                               stream()), "dmt_dense_fwd")
+    return Y, Y_pre
+
+
+def dense_bwd_x(dY, W, A_prev, act_prev, keep=None, keep_scale=1.0):
+    m, n = dY.shape
+    k = W.shape[1]
+    dX = torch.empty(m, k, device=dY.device, dtype=torch.float32)
+    check(load().dmt_dense_bwd_x(ptr(dY), ptr(W), ptr(A_prev), ptr(keep), float(keep_scale), ptr(dX), m, n, k,
+                                 act_prev, stream()), "dmt_dense_bwd_x")
+    return dX
+
+
+def dense_bwd_w(dY, X, want_bias=True):
+    m, n = dY.shape
+    k = X.shape[1]
+    dW = torch.empty(n, k, device=dY.device, dtype=torch.float32)
+    db = torch.empty(n, device=dY.device, dtype=torch.float32) if want_bias else None
+    check(load().dmt_dense_bwd_w(ptr(dY), ptr(X), ptr(dW), ptr(db), m, n, k, stream()), "dmt_dense_bwd_w")
+    return dW, db
+
+
+def ae_encoder_fwd(rows, indptr, indices, val, W1t, b1):
+    H = W1t.shape[1]
+    A1 = torch.empty(rows.numel(), H, device=W1t.device, dtype=torch.float32)
+    check(load().dmt_ae_encoder_fwd(ptr(rows), rows.numel(), ptr(indptr), ptr(indices), ptr(val), ptr(W1t), ptr(b1),
+                                    H, ptr(A1), stream()), "dmt_ae_encoder_fwd")
+    return A1
+
+
+def ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, loss_kind, nnz, train):
+    """pred is aligned with the target CSR (length nnz). Train mode also returns gout (same alignment),
+    dZ3 [rows x H] and the per-row loss sums."""
+    dev = A3.device
+    H = A3.shape[1]
+    pred = torch.zeros(nnz, device=dev, dtype=torch.float32)
+    gout = dz3 = loss_rows = n_t = None
+    if train:
+        gout = torch.zeros(nnz, device=dev, dtype=torch.float32)
+        dz3 = torch.empty_like(A3)
+        loss_rows = torch.empty(rows.numel(), device=dev, dtype=torch.float32)
+        ip = indptr.to(torch.int64)
+        r = rows.to(torch.int64)
+        n_t = (ip[r + 1] - ip[r]).sum().to(torch.int32).reshape(1)
+    check(load().dmt_ae_decoder_fwd(ptr(rows), rows.numel(), ptr(indptr), ptr(indices), ptr(target), ptr(A3), ptr(W4),
+                                    ptr(b4), H, loss_kind, ptr(n_t), ptr(pred), ptr(gout), ptr(dz3), ptr(loss_rows),
+                                    stream()), "dmt_ae_decoder_fwd")
+    return pred, gout, dz3, loss_rows, n_t
+
+
+class Org:
+    """Handle of the device-resident organization engine (dmt_org_*)."""
+
+    def __init__(self, n_rows, n_enc, n_dec, H1, H2, d_csr, t_csr, batch_rows, loss_kind, own_stream=True):
+        lib = load()
+        self._lib = lib
+        self.d_csr = d_csr  # (indptr, indices, val) int32/int32/float32 CUDA tensors, kept alive here
+        self.t_csr = t_csr  # (indptr, indices)
+        self.h = C.c_void_p()
+        st = None if own_stream else stream()
+        check(lib.dmt_org_create(C.byref(self.h), n_rows, n_enc, n_dec, H1, H2, ptr(d_csr[0]), ptr(d_csr[1]),
+                                 ptr(d_csr[2]), d_csr[1].numel(), ptr(t_csr[0]), ptr(t_csr[1]), t_csr[1].numel(),
+                                 batch_rows, loss_kind, st), "dmt_org_create")
+        self.n_params = lib.dmt_org_num_params(self.h)
+        self.H2 = H2
+        self._target = None
+
+    def set_params(self, flat):
+        check(self._lib.dmt_org_set_params(self.h, ptr(flat)), "dmt_org_set_params")
+
+    def get_params(self, out=None):
+        out = torch.empty(self.n_params, device=self.d_csr[0].device, dtype=torch.float32) if out is None else out
+        check(self._lib.dmt_org_get_params(self.h, ptr(out)), "dmt_org_get_params")
+        return out
+
+    def set_target(self, t_val):
+        self._target = t_val
+        check(self._lib.dmt_org_set_target(self.h, ptr(t_val)), "dmt_org_set_target")
+
+    def train_epoch(self, rows, row_off, n_t_entries, n_d_entries, keep=None, seed=0, lr=1e-3, betas=(0.9, 0.999),
+                    eps=1e-8, weight_decay=5e-4, max_norm=1.0, epoch_loss=None):
+        nb = row_off.numel() - 1
+        check(self._lib.dmt_org_train_epoch(self.h, ptr(rows), ptr(row_off), rows.numel(), nb, int(n_t_entries),
+                                            int(n_d_entries), ptr(keep), int(seed), float(lr), float(betas[0]),
+                                            float(betas[1]), float(eps), float(weight_decay), float(max_norm),
+                                            ptr(epoch_loss)), "dmt_org_train_epoch")
+
+    def predict(self, d_csr, t_csr, n_rows, out):
+        check(self._lib.dmt_org_predict(self.h, ptr(d_csr[0]), ptr(d_csr[1]), ptr(d_csr[2]), ptr(t_csr[0]),
+                                        ptr(t_csr[1]), n_rows, ptr(out)), "dmt_org_predict")
+        return out
+
+    def sync(self):
+        check(self._lib.dmt_org_sync(self.h), "dmt_org_sync")
+
+    def wait_current(self):
+        """The organization's stream waits for work already enqueued on torch's current stream."""
+        check(self._lib.dmt_org_wait_stream(self.h, stream()), "dmt_org_wait_stream")
+
+    def signal_current(self):
+        """torch's current stream waits for work already enqueued on the organization's stream."""
+        check(self._lib.dmt_org_signal_stream(self.h, stream()), "dmt_org_signal_stream")
+
+    def cuda_stream(self):
+        return self._lib.dmt_org_stream(self.h)
+
+    def close(self):
+        if self.h:
+            self._lib.dmt_org_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

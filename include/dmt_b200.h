@@ -1,0 +1,204 @@
+/*
+ * dmt_b200.h — C-ABI of the B200-native DMTCDR hot path (libdmt_b200.so, sm_100a only).
+ *
+ * The reference (diaoenmao/Decentralized-Multi-Target-Cross-Domain-Recommendation-...) is pure Python on
+ * PyTorch; it has no FFI of its own. These entry points are what a binding for its hot path attaches to
+ * (INTEGRATION.md shows the ctypes stub). Each one cites the reference code it replaces as
+ * `src/<file>:<lines>`.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - every function returns int: 0 = ok, < 0 = DMT_E_* below, > 0 = a cudaError_t value.
+ *     Nothing throws or aborts. dmt_last_error() returns a static message for the calling thread.
+ *   - all kernels are asynchronous on the given stream and re-entrant across streams; the only state is
+ *     inside the opaque handles (dmt_plan_t, dmt_org_t).
+ *   - floating point is fp32 (as the reference); indices are int32 after ingestion (the reference's int64
+ *     indices are narrowed once at the API edge); pointer-offset arrays (indptr) are int32, nnz < 2^31.
+ *   - "rows" are the aligned entity (users in data_mode 'user', items in 'item'); "columns" the other one.
+ */
+#ifndef DMT_B200_H
+#define DMT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMT_E_ARG (-1)      /* invalid argument */
+#define DMT_E_STATE (-2)    /* handle used in the wrong state */
+#define DMT_E_NOMEM (-3)    /* host allocation failed */
+#define DMT_E_ARCH (-4)     /* device is not sm_100 */
+
+#define DMT_LOSS_MSE 0 /* explicit: (o-y)^2            src/models/utils.py:11 */
+#define DMT_LOSS_BCE 1 /* implicit: BCE with logits     src/models/utils.py:9  */
+
+const char* dmt_last_error(void);
+int dmt_version(void);
+/* 0 when the current device is a compute-capability 10.x part, DMT_E_ARCH otherwise. */
+int dmt_check_device(void);
+
+/* ------------------------------------------------------------------ MTAL coordinator (src/assist.py) */
+
+/* Pseudo-residual r = -dL/dF of the summed loss (src/assist.py:45-58):
+ * MSE: 2(y-F); BCE: y - sigmoid(F); clamped to [-clamp, clamp] when clamp > 0 (src/assist.py:51-56). */
+int dmt_residual(const float* F, const float* y, float* r, int64_t n, int loss_kind, float clamp, void* stream);
+
+/* One streaming pass of Assist.update's apply step for ALL owners (src/assist.py:131-176 +
+ * src/models/assist.py:36-37):  F_new[p] = F_old[p] + rate_col[col[p]] * sum_j S[owner[col[p]]][j] * O'[j][p]
+ * with O'[j][p] = O[j][p] if p < match_end[owner] else O[owner][p]   (partial alignment, src/assist.py:95-103).
+ * O is org-major [K][nnz]; S is the row-wise softmax of every owner's assistance weights, [K][K] row-major;
+ * rate_col[c] = assist_rate of the owner of column c at c's local index. */
+int dmt_assist_combine(const float* F_old, const float* O, const int32_t* col, const int32_t* owner,
+                       const float* rate_col, const float* S, const int64_t* match_end, float* F_new,
+                       int64_t nnz, int K, void* stream);
+
+/* Gather one owner's view for the L-BFGS fit (src/assist.py:93-117): for e in [0,n): p = pos[e];
+ * h[e]=F_old[p], t[e]=y[p], V[j][e] = (rank[e] < n_match ? O[j][p] : O[owner][p]). pos is the owner's entries in
+ * column-sorted order, rank[e] the entry's rank in the original (row-major) order. V is [K][n]. */
+int dmt_assist_gather_view(const float* F_old, const float* y, const float* O, const int32_t* pos,
+                           const int32_t* rank, int64_t nnz, int64_t n, int K, int owner, int64_t n_match, float* h,
+                           float* t, float* V, void* stream);
+
+/* Fused loss + gradient of models.Assist for one owner (src/models/assist.py:25-40, closure src/assist.py:121-126).
+ * Entries are column-sorted; seg_off[n_rate+1] delimits the entries of each owned column (local index = segment).
+ * loss = mean_e l(h_e + rate[c(e)] * sum_j softmax(w)_j V[j][e], t_e);
+ * out[0]=loss, d_rate[n_rate], d_w[K] (gradient w.r.t. the UN-normalised weights w). scratch >= dmt_assist_scratch_floats(K). */
+int64_t dmt_assist_scratch_floats(int K);
+int dmt_assist_loss_grad(const float* h, const float* t, const float* V, const int32_t* seg_off, const float* rate,
+                         const float* w, int64_t n, int n_rate, int K, int loss_kind, float* out_loss, float* d_rate,
+                         float* d_w, float* scratch, void* stream);
+
+/* Round-0 predictor models.Base (src/models/base.py:22-60). fit: base[idx] += rating, count[idx] += 1.
+ * predict (explicit): base/(count+1e-10), unseen columns -> mean of the seen means (fill computed here);
+ * predict (implicit): base / scalar_count, scalar_count = sum over fitted batches of #distinct rows (base.py:35-37). */
+int dmt_base_fit(const int32_t* idx, const float* rating, int64_t n, float* base, float* count, void* stream);
+int dmt_base_predict(const float* base, const float* count, int32_t n_cols, const int32_t* target_idx, int64_t n,
+                     int implicit, float implicit_count, float* out, float* scratch /* >= 2 floats */, void* stream);
+
+/* ------------------------------------------------------------------ sort-by-index + segmented reduction */
+
+/* Stable sort of keys (values in [0, key_bound)) -> perm (source positions in sorted order), unique keys,
+ * segment offsets and the segment count (device int32). Replaces torch.sort/unique_consecutive at
+ * src/models/ae.py:103-104,137-139 and the implicit sort inside embedding_dense_backward.
+ * temp: device scratch of dmt_sort_segments_temp_bytes(n) bytes. seg_key/seg_off need n and n+1 slots. */
+int64_t dmt_sort_segments_temp_bytes(int64_t n);
+int dmt_sort_segments(const int32_t* keys, int64_t n, int32_t key_bound, int32_t* perm, int32_t* seg_key,
+                      int32_t* seg_off, int32_t* n_seg, void* temp, int64_t temp_bytes, void* stream);
+
+/* grad[seg_key[s]][:] = sum_{e in segment s} coef[perm[e]] * src[src_row[perm[e]]][:]   (width floats per row),
+ * bias_grad[seg_key[s]] = sum coef (may be NULL). One warp per segment, no atomics: the dense-gradient form of
+ * autograd's embedding / index backward (src/models/mf.py:37,44; src/models/ae.py:102,135). Rows of grad that
+ * own no segment are NOT touched (zero them first). n_seg is read from device memory. */
+int dmt_segment_reduce_rows(const int32_t* perm, const int32_t* seg_key, const int32_t* seg_off, const int32_t* n_seg,
+                            int64_t n_seg_max, const float* coef, const int32_t* src_row, const float* src, int width,
+                            float* grad, float* bias_grad, void* stream);
+
+/* ------------------------------------------------------------------ optimizer (src/utils.py:253-254, src/organization.py:161-162) */
+
+/* sum of squares of g[0..n) -> out[0] (deterministic two-stage); scratch >= dmt_sqnorm_scratch_floats() floats. */
+int64_t dmt_sqnorm_scratch_floats(void);
+int dmt_sqnorm(const float* g, int64_t n, float* out, float* scratch, void* stream);
+/* clip_grad_norm_(params, max_norm) fused into torch.optim.Adam(lr, betas, eps, weight_decay) (dense, L2):
+ * coef = min(1, max_norm/(sqrt(*sqnorm)+1e-6)); g' = coef*g + wd*w; m,v update; w -= lr/(1-b1^t) * m/(sqrt(v)/sqrt(1-b2^t)+eps).
+ * sqnorm (device) may be NULL = no clipping. step is the 1-based step count t. scratch >= 4 floats (device). */
+int dmt_adam_clip_step(float* w, const float* g, float* m, float* v, int64_t n, const float* sqnorm, float max_norm,
+                       double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                       float* scratch, void* stream);
+
+/* ------------------------------------------------------------------ MF / GMF (src/models/mf.py, GMF branch of nmf.py) */
+
+/* MF forward + loss + per-rating dloss/dpred in one pass (src/models/mf.py:36-48,79-92):
+ *   pred = sum_d (Wu[u,d]+bu[u]) (Wi[i,d]+bi[i])  [+ u~.pu[e]] [+ i~.pi[e]]  + bias
+ * pu/pi: optional per-rating side-information projections [n x H] (outputs of the user_profile / item_attr Linear)
+ * or NULL. H in {128,256,384,512}. dpred may be NULL (eval). sums[0] = sum of per-rating losses (mean = /n),
+ * sums[1] = sum of dloss/dpred. scratch >= dmt_mf_scratch_floats() floats. */
+int64_t dmt_mf_scratch_floats(void);
+int dmt_mf_fwd(const int32_t* user, const int32_t* item, const float* rating, int64_t n, const float* Wu,
+               const float* Wi, const float* bu, const float* bi, const float* bias, const float* pu, const float* pi,
+               int H, int loss_kind, float* pred, float* dpred, float* sums, float* scratch, void* stream);
+/* Dense gradient of one embedding table and its bias table from the ratings sorted by that table's index
+ * (perm/seg_* from dmt_sort_segments on user[] or item[]):
+ *   dW[r] = sum_{e: key(e)=r} g_e * (W_other[other[e]] + b_other[other[e]] [+ p_side[e]]),  db[r] = row-sum of dW[r],
+ * g_e = dpred[e]*grad_scale. Rows without ratings are not touched (zero dW/db first). */
+int dmt_mf_bwd_table(const int32_t* other, const float* W_other, const float* b_other, const float* p_side, int H,
+                     const float* dpred, float grad_scale, const int32_t* perm, const int32_t* seg_key,
+                     const int32_t* seg_off, const int32_t* n_seg, int64_t n_seg_max, float* dW, float* db,
+                     void* stream);
+/* d_p[e][:] = g_e * (W[idx[e]] + b[idx[e]]): gradient w.r.t. a side-information projection (src/models/mf.py:82-90). */
+int dmt_mf_bwd_side(const int32_t* idx, int64_t n, const float* W, const float* b, int H, const float* dpred,
+                    float grad_scale, float* d_p, void* stream);
+
+/* ------------------------------------------------------------------ AAE (src/models/ae.py:98-157) */
+
+/* Dense layer forward  Y = act(X W^T + b) [* keep*keep_scale]: X [m x k], W [n x k] (nn.Linear layout), act: 0 none,
+ * 1 tanh, 2 relu. keep (uint8 [m x n], 0/1) may be NULL; when given Y_pre receives the pre-dropout activation
+ * and Y the dropped one (src/models/ae.py:14-19,44-45,132). */
+int dmt_dense_fwd(const float* X, const float* W, const float* b, float* Y, float* Y_pre, const uint8_t* keep,
+                  float keep_scale, int m, int n, int k, int act, void* stream);
+/* dX = (dY W) * dact(A_prev) [* keep*keep_scale]:  dY [m x n], W [n x k], A_prev [m x k] = activation that fed
+ * this layer (act_prev 1: 1-a^2; 2: a>0; 0 or A_prev NULL: none). */
+int dmt_dense_bwd_x(const float* dY, const float* W, const float* A_prev, const uint8_t* keep, float keep_scale,
+                    float* dX, int m, int n, int k, int act_prev, void* stream);
+/* dW = dY^T X  [n x k], db = column sums of dY [n] (db may be NULL). */
+int dmt_dense_bwd_w(const float* dY, const float* X, float* dW, float* db, int m, int n, int k, void* stream);
+
+/* Encoder first layer as CSR SpMM (src/models/ae.py:101-110): for batch row j (row id rows[j]):
+ * A1[j] = tanh(b1 + sum_{e in CSR row} val[e] * W1t[col[e]])   W1t = encoder_linear.weight^T, [n_cols x H]. */
+int dmt_ae_encoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices,
+                       const float* val, const float* W1t, const float* b1, int H, float* A1, void* stream);
+/* Decoder last layer + loss + first backward product in one pass over the target rows (src/models/ae.py:135-142,153-156):
+ * for each target entry e (CSR position) of batch row j: o = A3[j].W4[c_e] + b4[c_e]; pred[e] = o (pred may be NULL);
+ * train mode (gout != NULL): gout[e] = dloss/do / *n_targets, dZ3[j] = (sum_e gout[e] W4[c_e]) * (1 - A3[j]^2),
+ * loss_rows[j] = sum_e loss. H in {128,256,384,512}. */
+int dmt_ae_decoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices,
+                       const float* target, const float* A3, const float* W4, const float* b4, int H, int loss_kind,
+                       const int32_t* n_targets, float* pred, float* gout, float* dZ3, float* loss_rows, void* stream);
+
+/* ------------------------------------------------------------------ device-resident organization engine */
+
+typedef struct dmt_org dmt_org_t;
+
+/* One organization's AAE with its data resident in HBM (Organization.train/predict, src/organization.py:140-217).
+ * data CSR: n_rows x n_enc (the organization's own columns, local ids); target CSR: n_rows x n_dec (ALL columns;
+ * values = residuals, set every round with dmt_org_set_target). The CSR arrays are borrowed device pointers that
+ * must outlive the handle; hidden sizes are the reference's [H1=256, H2=128] (src/utils.py:166-171).
+ * stream NULL: the handle creates a private non-blocking stream (organizations then run concurrently). */
+int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, int H2, const int32_t* d_indptr,
+                   const int32_t* d_indices, const float* d_val, int64_t d_nnz, const int32_t* t_indptr,
+                   const int32_t* t_indices, int64_t t_nnz, int batch_rows, int loss_kind, void* stream);
+int dmt_org_destroy(dmt_org_t* org);
+/* number of fp32 parameters; flat layout: W1t[n_enc*H1] b1[H1] W2[H2*H1] b2[H2] W3[H1*H2] b3[H1] W4[n_dec*H1] b4[n_dec] */
+int64_t dmt_org_num_params(const dmt_org_t* org);
+/* Copy parameters in/out (device pointers, flat layout above). set also resets the Adam state: the reference builds
+ * a fresh model and optimizer every round (src/organization.py:144-148). */
+int dmt_org_set_params(dmt_org_t* org, const float* flat);
+int dmt_org_get_params(const dmt_org_t* org, float* flat);
+/* Target values for the coming rounds (borrowed device pointer aligned with t_indices; keep it stable, its address
+ * is part of the captured graph). */
+int dmt_org_set_target(dmt_org_t* org, const float* t_val);
+/* One local epoch = one CUDA-graph launch. Batch b = rows[row_off[b] .. row_off[b+1]) (device int32; every batch
+ * sorted ascending, rows with neither data nor targets removed = the reference's `total_user`, ae.py:101).
+ * Batches without DATA entries are skipped on device (src/organization.py:153-155). n_t_entries / n_d_entries:
+ * total target / data entries of the listed rows. keep: optional uint8 [n_rows_total x H2] dropout keep-masks in
+ * batch-row order (parity mode); NULL = counter-based on-device generator seeded with `seed`.
+ * epoch_loss[b] (device, may be NULL) receives each batch's mean loss. Asynchronous on the handle's stream. */
+int dmt_org_train_epoch(dmt_org_t* org, const int32_t* rows, const int32_t* row_off, int n_rows_total, int n_batches,
+                        int64_t n_t_entries, int64_t n_d_entries, const uint8_t* keep, uint64_t seed, double lr,
+                        double beta1, double beta2, double eps, double weight_decay, float max_norm,
+                        float* epoch_loss);
+/* Organization.predict: eval forward at every target position of the given (data, target-structure) pair — pass the
+ * test split's CSR to predict it — writing pred aligned with t_indices. */
+int dmt_org_predict(dmt_org_t* org, const int32_t* d_indptr, const int32_t* d_indices, const float* d_val,
+                    const int32_t* t_indptr, const int32_t* t_indices, int n_rows, float* pred);
+int dmt_org_sync(dmt_org_t* org);
+void* dmt_org_stream(dmt_org_t* org);
+/* Stream ordering with the caller's streams: wait = the handle's stream waits for work already enqueued on
+ * `stream`; signal = `stream` waits for work already enqueued on the handle's stream. */
+int dmt_org_wait_stream(dmt_org_t* org, void* stream);
+int dmt_org_signal_stream(dmt_org_t* org, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMT_B200_H */

@@ -1,0 +1,288 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle (oracle/) on seeded inputs.
+
+Bit-exact for integer/index results (sort permutation, segment keys/offsets/counts); fp32 results within the
+tolerance written next to each check (different summation order than the oracle's dense formulation).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as om
+from oracle import mtal, train
+from golden_io import Fixture, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import native
+
+    native.load()
+    assert native.load().dmt_check_device() == 0
+    return native
+
+
+def cu(x, dtype=None):
+    t = torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+@pytest.mark.parametrize("kind,clamp", [("explicit", 0.0), ("explicit", 1.0), ("implicit", 1.0), ("implicit", 0.0)])
+@pytest.mark.parametrize("n", [0, 1, 5, 4099])
+def test_residual(nat, kind, clamp, n):
+    g = torch.Generator().manual_seed(n)
+    F = torch.randn(n, generator=g) * 3
+    y = torch.randint(0, 2, (n,), generator=g).float() if kind == "implicit" else torch.randint(1, 6, (n,), generator=g).float()
+    ref = mtal.residual(F, y, kind, clamp > 0)
+    got = nat.residual(cu(F), cu(y), nat.LOSS_KIND[kind], clamp).cpu().numpy()
+    assert np.abs(got - ref).max(initial=0) <= 2e-7 * max(1.0, np.abs(ref).max(initial=0))
+
+
+@pytest.mark.parametrize("n,bound", [(0, 7), (1, 1), (1000, 13), (70000, 3706), (50000, 48178)])
+def test_sort_segments_bit_exact(nat, n, bound):
+    g = torch.Generator().manual_seed(n + bound)
+    keys = torch.randint(0, bound, (n,), generator=g, dtype=torch.int32)
+    perm, seg_key, seg_off, n_seg = nat.sort_segments(cu(keys), bound)
+    ref_sorted, ref_perm = torch.sort(keys.long(), stable=True)
+    uniq, counts = torch.unique_consecutive(ref_sorted, return_counts=True)
+    ns = int(n_seg.item())
+    assert ns == len(uniq)
+    assert torch.equal(perm[:n].cpu().long(), ref_perm)
+    assert torch.equal(seg_key[:ns].cpu().long(), uniq)
+    off = torch.zeros(ns + 1, dtype=torch.long)
+    off[1:] = torch.cumsum(counts, 0)
+    assert torch.equal(seg_off[:ns + 1].cpu().long(), off)
+
+
+@pytest.mark.parametrize("width", [128, 256])
+def test_segment_reduce_rows(nat, width):
+    g = torch.Generator().manual_seed(width)
+    n, n_rows_out, n_src = 5000, 97, 40
+    keys = torch.randint(0, n_rows_out, (n,), generator=g, dtype=torch.int32)
+    keys[keys == 5] = 6  # leave row 5 empty
+    coef = torch.randn(n, generator=g)
+    src_row = torch.randint(0, n_src, (n,), generator=g, dtype=torch.int32)
+    src = torch.randn(n_src, width, generator=g)
+    seg = nat.sort_segments(cu(keys), n_rows_out)
+    grad = torch.zeros(n_rows_out, width).cuda()
+    bgrad = torch.zeros(n_rows_out).cuda()
+    nat.segment_reduce_rows(*seg, n_rows_out, cu(coef), cu(src_row), cu(src), grad, bgrad)
+    ref = torch.zeros(n_rows_out, width).index_add_(0, keys.long(), coef[:, None] * src[src_row.long()])
+    refb = torch.zeros(n_rows_out).index_add_(0, keys.long(), coef)
+    assert rel_err(grad.cpu(), ref) < 1e-5
+    assert rel_err(bgrad.cpu(), refb) < 1e-5
+    assert float(grad[5].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n", [7, 1_000_003])
+def test_sqnorm_and_adam(nat, n):
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(n, generator=g) * 0.1
+    opt = train.Adam({"w": w.clone()})
+    wd, md, vd = cu(w.clone()), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g) * (0.01 if step == 2 else 1.0)
+        coef, total = train.clip_coef([grad])
+        opt.step({"w": grad}, coef)
+        gd = cu(grad)
+        sq = nat.sqnorm(gd)
+        assert abs(float(sq) - total ** 2) <= 1e-5 * total ** 2
+        nat.adam_clip_step(wd, gd, md, vd, step, sq, 1.0)
+    assert rel_err(wd.cpu(), opt.p["w"]) < 1e-5
+    assert rel_err(md.cpu(), opt.m["w"]) < 1e-5
+    assert rel_err(vd.cpu(), opt.v["w"]) < 1e-5
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("m,n,k", [(1, 128, 256), (37, 128, 256), (500, 256, 128), (700, 64, 100), (6040, 128, 256)])
+def test_dense_layers(nat, act, m, n, k):
+    g = torch.Generator().manual_seed(m * n + k)
+    X = torch.randn(m, k, generator=g)
+    W = torch.randn(n, k, generator=g) / k ** 0.5
+    b = torch.randn(n, generator=g) * 0.1
+    keep = (torch.rand(m, n, generator=g) < 0.5).to(torch.uint8)
+    f = [lambda z: z, torch.tanh, torch.relu][act]
+    Xr, Wr, br = X.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    pre = f(Xr @ Wr.t() + br)
+    Yr = pre * keep.float() * 2.0
+    dY = torch.randn(m, n, generator=g)
+    Yr.backward(dY)
+    Y, Y_pre = nat.dense_fwd(cu(X), cu(W), cu(b), act, cu(keep), 2.0)
+    assert rel_err(Y.cpu(), Yr.detach()) < 2e-6
+    assert rel_err(Y_pre.cpu(), pre.detach()) < 2e-6
+    # backward of this layer: dZ = dY * keep*2 * act'(pre)
+    dact = [torch.ones_like(pre), 1 - pre.detach() ** 2, (pre.detach() > 0).float()][act]
+    dZ = dY * keep.float() * 2.0 * dact
+    dW, db = nat.dense_bwd_w(cu(dZ), cu(X))
+    assert rel_err(dW.cpu(), Wr.grad) < 1e-5
+    assert rel_err(db.cpu(), br.grad) < 1e-5
+    # dX through a previous activation A_prev (here: X itself taken as tanh output of an earlier layer)
+    Aprev = torch.tanh(torch.randn(m, k, generator=g))
+    dX = nat.dense_bwd_x(cu(dZ), cu(W), cu(Aprev), 1)
+    assert rel_err(dX.cpu(), (dZ @ W) * (1 - Aprev ** 2)) < 1e-5
+
+
+def _rand_csr(g, n_rows, n_cols, density, empty_rows=()):
+    dense = (torch.rand(n_rows, n_cols, generator=g) < density)
+    for r in empty_rows:
+        dense[r] = False
+    val = torch.randint(1, 6, (n_rows, n_cols), generator=g).float() * dense
+    from scipy.sparse import csr_matrix
+
+    return csr_matrix(val.numpy())
+
+
+@pytest.mark.parametrize("loss", ["explicit", "implicit"])
+def test_ae_encoder_decoder_kernels(nat, loss):
+    """encoder SpMM and decoder SDDMM+loss+dZ3 against the oracle's dense algebra (src/models/ae.py:98-157)."""
+    g = torch.Generator().manual_seed(11)
+    n_rows, n_enc, n_dec, H = 70, 45, 150, 256
+    D = _rand_csr(g, n_rows, n_enc, 0.1, empty_rows=(3, 4))
+    T = _rand_csr(g, n_rows, n_dec, 0.3, empty_rows=(4, 9))
+    if loss == "implicit":
+        T.data = (T.data >= 3.5).astype(np.float32)
+    W1t = torch.randn(n_enc, H, generator=g) * 0.1
+    b1 = torch.randn(H, generator=g) * 0.1
+    rows = torch.arange(n_rows, dtype=torch.int32)
+    A1 = nat.ae_encoder_fwd(cu(rows), cu(D.indptr, torch.int32), cu(D.indices, torch.int32), cu(D.data), cu(W1t), cu(b1))
+    ref = torch.tanh(torch.from_numpy(D.toarray()) @ W1t + b1)
+    assert rel_err(A1.cpu(), ref) < 2e-6
+    A3 = torch.tanh(torch.randn(n_rows, H, generator=g))
+    W4 = torch.randn(n_dec, H, generator=g) * 0.1
+    b4 = torch.randn(n_dec, generator=g) * 0.1
+    A3r, W4r = A3.clone().requires_grad_(True), W4.clone()
+    rt = torch.from_numpy(np.repeat(np.arange(n_rows), np.diff(T.indptr))).long()
+    ct = torch.from_numpy(T.indices).long()
+    y = torch.from_numpy(T.data)
+    pred_ref = (A3r[rt] * W4r[ct]).sum(-1) + b4[ct]
+    loss_ref = om.loss_fn(pred_ref, y, loss)
+    gout_ref, = torch.autograd.grad(loss_ref, pred_ref, retain_graph=True)
+    dA3_ref, = torch.autograd.grad(loss_ref, A3r)
+    pred, gout, dz3, loss_rows, n_t = nat.ae_decoder_fwd(cu(rows), cu(T.indptr, torch.int32), cu(T.indices, torch.int32),
+                                                         cu(T.data), cu(A3), cu(W4), cu(b4), nat.LOSS_KIND[loss],
+                                                         T.nnz, True)
+    assert int(n_t) == T.nnz
+    assert rel_err(pred.cpu(), pred_ref.detach()) < 2e-6
+    assert rel_err(gout.cpu(), gout_ref) < 1e-5
+    assert abs(float(loss_rows.sum()) / T.nnz - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+    assert rel_err(dz3.cpu(), dA3_ref * (1 - A3 ** 2)) < 1e-5
+    pred_e, *_ = nat.ae_decoder_fwd(cu(rows), cu(T.indptr, torch.int32), cu(T.indices, torch.int32), None, cu(A3),
+                                    cu(W4), cu(b4), nat.LOSS_KIND[loss], T.nnz, False)
+    assert rel_err(pred_e.cpu(), pred_ref.detach()) < 2e-6
+
+
+@pytest.mark.parametrize("case", ["model_mf_user_explicit", "model_mf_user_implicit_info1"])
+def test_mf_kernels_vs_golden(nat, case):
+    """MF forward/loss and dense embedding gradients against the reference's own outputs (golden fixture)."""
+    fx = Fixture(case)
+    sd = fx.group("sd0")
+    kind = nat.LOSS_KIND[fx.meta["target_mode"]]
+    for j in (0, 1):
+        b = fx.group("b{}/in".format(j))
+        user, item, rating = cu(b["user"], torch.int32), cu(b["item"], torch.int32), cu(b["rating"])
+        Wu, Wi = cu(sd["user_weight.weight"]), cu(sd["item_weight.weight"])
+        bu, bi = cu(sd["user_bias.weight"].view(-1)), cu(sd["item_bias.weight"].view(-1))
+        pu = None
+        if "user_profile" in b:
+            pu, _ = nat.dense_fwd(cu(b["user_profile"]), cu(sd["user_profile.weight"]), cu(sd["user_profile.bias"]), 0)
+        pred, dpred, sums = nat.mf_fwd(user, item, rating, Wu, Wi, bu, bi, cu(sd["bias"]), kind, pu=pu)
+        n = user.numel()
+        assert rel_err(pred.cpu(), fx["b{}/train/target_rating".format(j)]) < 2e-5
+        ref_loss = float(fx["b{}/train/loss".format(j)])
+        assert abs(float(sums[0]) / n - ref_loss) <= 1e-5 * abs(ref_loss)
+        scale = 1.0 / n
+        seg_u = nat.sort_segments(user, Wu.shape[0])
+        seg_i = nat.sort_segments(item, Wi.shape[0])
+        dWu, dbu = nat.mf_bwd_table(item, Wi, bi, pu, dpred, scale, seg_u, Wu.shape[0])
+        dWi, dbi = nat.mf_bwd_table(user, Wu, bu, None, dpred, scale, seg_i, Wi.shape[0])
+        G = fx.group("b{}/grad".format(j), as_torch=False)
+        assert rel_err(dWu.cpu(), G["user_weight.weight"]) < 5e-5
+        assert rel_err(dWi.cpu(), G["item_weight.weight"]) < 5e-5
+        assert rel_err(dbu.cpu(), G["user_bias.weight"].reshape(-1)) < 5e-5
+        assert rel_err(dbi.cpu(), G["item_bias.weight"].reshape(-1)) < 5e-5
+        assert abs(float(sums[1]) * scale - float(G["bias"][0])) <= 5e-5 * max(1e-6, abs(float(G["bias"][0])))
+        if pu is not None:
+            d_pu = nat.mf_bwd_side(user, Wu, bu, dpred, scale)
+            dWp, dbp = nat.dense_bwd_w(d_pu, cu(b["user_profile"]))
+            assert rel_err(dWp.cpu(), G["user_profile.weight"]) < 5e-5
+            assert rel_err(dbp.cpu(), G["user_profile.bias"]) < 5e-5
+
+
+@pytest.mark.parametrize("case", ["mtal_douban_user_explicit", "mtal_amazon_user_implicit_dp", "mtal_ml_user_explicit"])
+def test_combine_and_fit_kernels_vs_golden(nat, case):
+    """dmt_assist_combine for every constant-rate variant and the fused loss+grad closure against autograd."""
+    fx = Fixture(case)
+    m = fx.meta
+    kind = nat.LOSS_KIND[m["target_mode"]]
+    K = m["num_organizations"]
+    y = fx.csr("y/train")
+    n_cols = y.shape[1]
+    split = [fx["data_split/{}".format(i)] for i in range(K)]
+    views = mtal.owner_views(y.indices, split, n_cols)
+    owner = np.full(n_cols, -1, np.int32)
+    local = np.zeros(n_cols, np.int32)
+    for i, s in enumerate(split):
+        owner[s] = i
+        local[s] = np.arange(len(s))
+    F0 = fx.csr("F0/train").data
+    O = np.stack([fx["r1/org_out/train/{}".format(j)] for j in range(K)])
+    for name, v in fx.json("variants").items():
+        if v["ar_mode"] != "constant" or v["aw_mode"] != "constant":
+            continue
+        rate_col = np.full(n_cols, m["assist"]["ar"], np.float32)
+        S = np.full((K, K), 1.0 / K, np.float32)
+        match_end = None
+        if v["match_rate"] < 1:
+            ends = []
+            for i in range(K):
+                pos = views[i][0]
+                nm = int(len(pos) * v["match_rate"])
+                ends.append(pos[nm] if nm < len(pos) else y.nnz)
+            match_end = cu(np.array(ends, np.int64))
+        got = nat.assist_combine(cu(F0), cu(O), cu(y.indices, torch.int32), cu(owner), cu(rate_col), cu(S), match_end)
+        assert rel_err(got.cpu(), fx["update/{}/F1/train".format(name)]) < 2e-6, name
+    # fused closure: loss, d_rate, d_w for owner 0 against autograd on the oracle expression
+    i = 0
+    pos, idx = views[i]
+    order = np.argsort(idx, kind="stable")
+    n_rate = len(split[i])
+    seg_off = np.zeros(n_rate + 1, np.int32)
+    seg_off[1:] = np.cumsum(np.bincount(idx, minlength=n_rate))
+    n_match = int(len(pos) * 0.5)
+    h, t, V = nat.assist_gather_view(cu(F0), cu(y.data), cu(O), cu(pos[order], torch.int32), cu(order, torch.int32), i,
+                                     n_match)
+    g = torch.Generator().manual_seed(5)
+    rate = (torch.rand(n_rate, generator=g) * 0.5).requires_grad_(True)
+    w = torch.randn(K, generator=g).requires_grad_(True)
+    Oi = torch.from_numpy(O[:, pos].T.copy())
+    Oi[n_match:] = Oi[n_match:, i:i + 1]
+    _, loss = om.assist_forward(rate, w, torch.from_numpy(F0[pos]), Oi, torch.from_numpy(idx),
+                                torch.from_numpy(y.data[pos]), m["target_mode"])
+    loss.backward()
+    out = nat.assist_loss_grad(h, t, V, cu(seg_off), cu(rate.detach()), cu(w.detach()), kind).cpu()
+    assert abs(float(out[0]) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert rel_err(out[1:1 + n_rate], rate.grad) < 2e-5
+    assert rel_err(out[1 + n_rate:], w.grad) < 1e-4 or float((out[1 + n_rate:] - w.grad).abs().max()) < 1e-8
+
+
+@pytest.mark.parametrize("mode", ["explicit", "implicit"])
+def test_base_kernels(nat, mode):
+    g = torch.Generator().manual_seed(2)
+    n_cols, n = 60, 900
+    idx = torch.randint(0, n_cols - 3, (n,), generator=g)  # last 3 columns unseen
+    rating = torch.randint(1, 6, (n,), generator=g).float() if mode == "explicit" else torch.randint(0, 2, (n,), generator=g).float()
+    rows = torch.randint(0, 40, (n,), generator=g)
+    ref = om.Base(n_cols, mode)
+    ref.fit(idx, rating, rows)
+    tgt = torch.randint(0, n_cols, (500,), generator=g)
+    base = torch.zeros(n_cols).cuda()
+    count = torch.zeros(n_cols).cuda()
+    nat.base_fit(cu(idx, torch.int32), cu(rating), base, count)
+    got = nat.base_predict(base, count, cu(tgt, torch.int32), mode == "implicit", float(len(torch.unique(rows))))
+    assert rel_err(got.cpu(), ref.predict(tgt)) < 1e-6

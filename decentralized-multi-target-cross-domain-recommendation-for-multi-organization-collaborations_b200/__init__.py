@@ -9,3 +9,24 @@ Layout (only what the path needs):
   synth.py   synthetic ML1M/Douban/Amazon-shaped inputs
 """
 __version__ = "0.1.0"
+
+import os as _os
+import sys as _sys
+
+DROPIN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "dropin")
+
+
+def use_dropin():
+    """Put the host-side mirror of the reference interface first on sys.path and import it. Returns the three
+    modules the reference's drivers import by these exact top-level names: (models, organization, assist)."""
+    if DROPIN_DIR not in _sys.path:
+        _sys.path.insert(0, DROPIN_DIR)
+    import importlib
+
+    mods = []
+    for name in ("models", "organization", "assist"):
+        m = _sys.modules.get(name)
+        if m is not None and not getattr(m, "__file__", "").startswith(DROPIN_DIR):
+            raise ImportError("a different '{}' module is already imported from {}".format(name, m.__file__))
+        mods.append(importlib.import_module(name))
+    return tuple(mods)

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) ae_decoder_fwd_kernel(const int32_t* __re
                                                             const int32_t* __restrict__ ent_off,
                                                             float* __restrict__ pred, float* __restrict__ gout,
                                                             float* __restrict__ dZ3, float* __restrict__ loss_rows,
-                                                            BatchRef br) {
+                                                            int tanh_deriv, BatchRef br) {
     constexpr int H = VEC * 128;
     __shared__ float s_acc[8][H];
     __shared__ float s_loss[8];
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) ae_decoder_fwd_kernel(const int32_t* __re
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += s_acc[w][h];
         float av = A3[(int64_t)j * H + h];
-        dZ3[(int64_t)j * H + h] = s * (1.f - av * av);
+        dZ3[(int64_t)j * H + h] = tanh_deriv ? s * (1.f - av * av) : s;
     }
     if (threadIdx.x == 0) {
         float l = 0.f;
@@ -179,11 +179,11 @@ int launch_ae_encoder_fwd(const int32_t* rows, const int32_t* indptr, const int3
 int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
                           const float* A3, const float* W4, const float* b4, int H, int loss_kind,
                           const int32_t* n_targets, const int32_t* ent_off, float* pred, float* gout, float* dZ3,
-                          float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st) {
+                          float* loss_rows, int tanh_deriv, int n_rows_max, BatchRef br, cudaStream_t st) {
     if (n_rows_max <= 0) return 0;
 #define DMT_DEC(V)                                                                                              \
     ae_decoder_fwd_kernel<V><<<n_rows_max, 256, 0, st>>>(rows, indptr, indices, target, A3, W4, b4, loss_kind, \
-                                                         n_targets, ent_off, pred, gout, dZ3, loss_rows, br)
+                                                         n_targets, ent_off, pred, gout, dZ3, loss_rows, tanh_deriv, br)
     if (H == 128) DMT_DEC(1);
     else if (H == 256) DMT_DEC(2);
     else if (H == 384) DMT_DEC(3);
@@ -213,12 +213,13 @@ int dmt_ae_encoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, c
 int dmt_ae_decoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices,
                        const float* target, const float* A3, const float* W4, const float* b4, int H, int loss_kind,
                        const int32_t* n_targets, float* pred, float* gout, float* dZ3, float* loss_rows,
-                       void* stream) {
+                       int tanh_deriv, void* stream) {
     DMT_REQUIRE(n_rows >= 0, "dmt_ae_decoder_fwd: bad argument");
     DMT_REQUIRE(gout == nullptr || (n_targets && dZ3 && loss_rows && target), "dmt_ae_decoder_fwd: train mode needs "
                 "n_targets, target, dZ3 and loss_rows");
     return launch_ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, H, loss_kind, n_targets, nullptr, pred,
-                                 gout, dZ3, loss_rows, n_rows, batch_by_value(0, n_rows), as_stream(stream));
+                                 gout, dZ3, loss_rows, tanh_deriv, n_rows, batch_by_value(0, n_rows),
+                                 as_stream(stream));
 }
 
 }  // extern "C"

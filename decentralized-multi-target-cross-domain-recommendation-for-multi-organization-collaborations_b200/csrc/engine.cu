@@ -264,8 +264,8 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp) {
     DMT_CUDA(cudaMemsetAsync(G, 0, (size_t)o->n_params * sizeof(float), st));
     // decoder + loss + dZ3
     if ((rc = launch_ae_decoder_fwd(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1, DMT_LOSS_MSE,
-                                    o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, o->dz3, o->loss_rows, B, br,
-                                    st)))
+                                    o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, o->dz3, o->loss_rows, 1, B,
+                                    br, st)))
         return rc;
     // dW4, db4: segmented over (batch, target column)
     SegRef st4{o->pt.batch_seg_off, nullptr, b, 0, 0, o->n_dec};
@@ -483,7 +483,7 @@ int dmt_org_predict(dmt_org_t* o, const int32_t* d_indptr, const int32_t* d_indi
         if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, nullptr, nodrop, m, H2, H1, 1, br, st))) return rc;
         if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, m, H1, H2, 1, br, st))) return rc;
         if ((rc = launch_ae_decoder_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1, o->loss_kind,
-                                        nullptr, nullptr, pred, nullptr, nullptr, nullptr, m, br, st)))
+                                        nullptr, nullptr, pred, nullptr, nullptr, nullptr, 0, m, br, st)))
             return rc;
     }
     return 0;

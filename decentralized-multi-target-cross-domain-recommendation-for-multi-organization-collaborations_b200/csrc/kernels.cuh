@@ -70,7 +70,7 @@ int launch_ae_encoder_fwd(const int32_t* rows, const int32_t* indptr, const int3
 int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
                           const float* A3, const float* W4, const float* b4, int H, int loss_kind,
                           const int32_t* n_targets, const int32_t* ent_off, float* pred, float* gout, float* dZ3,
-                          float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st);
+                          float* loss_rows, int tanh_deriv, int n_rows_max, BatchRef br, cudaStream_t st);
 
 // ---- segments.cu
 struct SegRef {  // segments [seg_lo, seg_hi) either by value or from device batch_seg_off[b], [b+1]

@@ -1,0 +1,290 @@
+"""Drop-in ``organization`` module: ``Organization`` with the reference's surface
+(src/organization.py:21-217: ``initialize`` / ``train`` / ``predict`` and the attributes ``organization_id``,
+``data_split``, ``num_items``, ``model_name``, ``model_state_dict``), running on the device-resident engine.
+
+Inputs are the reference's dataset objects (``.data`` / ``.target`` scipy CSR in host memory, ``.num_users``,
+``.num_items``); outputs are fresh host objects (scipy CSR fp32, CPU state_dicts). Device buffers are owned here and
+reused across calls, keyed by the content of the CSR structure.
+"""
+import sys
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix
+
+from dmtcdr_b200 import engine as E
+from dmtcdr_b200 import native
+from dmtcdr_b200.config import cfg
+
+import models
+
+_DEVICE_CSR = {}
+
+
+def device_csr(m, with_values=True):
+    """Device copy of a scipy CSR, reused while the structure (and, if requested, the values) are unchanged."""
+    key = E.csr_key(m)
+    hit = _DEVICE_CSR.get(key)
+    if hit is None:
+        hit = E.DeviceCSR(m, _device(), with_values=False)
+        hit._values_crc = None
+        _DEVICE_CSR[key] = hit
+    if with_values:
+        host = np.ascontiguousarray(m.data, dtype=np.float32)
+        crc = E.zlib.crc32(host.view(np.uint8))
+        if hit._values_crc != crc:
+            hit.data = torch.from_numpy(host).to(_device())
+            hit._values_crc = crc
+    return hit
+
+
+def _device():
+    dev = str(cfg['device'])
+    if not dev.startswith('cuda'):
+        raise native.NativeError("dmtcdr_b200 has no CPU path: run with --device cuda (got '{}')".format(dev))
+    return dev
+
+
+def _rng_mode():
+    """'reference': consume torch's CPU generator exactly like the reference (data-loader seeds, parameter init,
+    dropout masks drawn on the host) so a run replays bit-for-bit comparable batches; 'device' (default): same
+    parameter init and sampler, dropout drawn by the on-device counter-based generator."""
+    return cfg['dmt_rng'] if 'dmt_rng' in cfg else 'device'
+
+
+def _shape_target():
+    if cfg['data_mode'] == 'user':
+        return (cfg['num_users']['target'], cfg['num_items']['target'])
+    if cfg['data_mode'] == 'item':
+        return (cfg['num_items']['target'], cfg['num_users']['target'])
+    raise ValueError('Not valid data mode')
+
+
+class LazyStateDict(dict):
+    """state_dict whose tensors are still on the organization's stream; materialised on first read."""
+
+    def __init__(self, flat, eng, n_enc, n_dec, H1, H2, on_ready=None):
+        super().__init__()
+        self._pending = (flat, eng, n_enc, n_dec, H1, H2, on_ready)
+
+    def _force(self):
+        p = self.__dict__.get('_pending')
+        if p is not None:
+            self.__dict__['_pending'] = None
+            flat, eng, n_enc, n_dec, H1, H2, on_ready = p
+            eng.sync()
+            sd = E.state_dict_from_flat(flat, n_enc, n_dec, H1, H2)
+            dict.update(self, {k: v.cpu() for k, v in sd.items()})
+            if on_ready is not None:
+                on_ready()
+        return self
+
+    def flat_device(self):
+        p = self.__dict__.get('_pending')
+        return p[0] if p is not None else None
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self._force(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self._force())
+
+    def __len__(self):
+        return dict.__len__(self._force())
+
+    def keys(self):
+        return dict.keys(self._force())
+
+    def items(self):
+        return dict.items(self._force())
+
+    def values(self):
+        return dict.values(self._force())
+
+    def __contains__(self, k):
+        return dict.__contains__(self._force(), k)
+
+    def __reduce__(self):
+        return (dict, (dict(self._force()),))
+
+
+class Organization:
+    def __init__(self, organization_id, data_split, model_name):
+        self.organization_id = organization_id
+        self.data_split = data_split
+        self.num_items = len(data_split)
+        self.model_name = model_name
+        self.model_state_dict = [None for _ in range(cfg['global']['num_epochs'] + 1)]
+
+    def __getstate__(self):
+        state = {k: v for k, v in self.__dict__.items() if not k.startswith('_')}
+        state['model_state_dict'] = [dict(s) if s is not None else None for s in self.model_state_dict]
+        return state
+
+    # ------------------------------------------------------------------ round 0
+    def initialize(self, dataset, metric, logger, iter):
+        """Round-0 baseline with models.base (src/organization.py:29-138)."""
+        mode = cfg['data_mode']
+        implicit = cfg['target_mode'] == 'implicit'
+        split = np.asarray(self.data_split, dtype=np.int64)
+        bs = cfg[self.model_name[iter]]['batch_size']['train']  # the loaders use the organization's model tag
+        output, target = {}, {}
+        dev = _device()
+        if _rng_mode() == 'reference':
+            np.random.seed(cfg['seed'])  # side effect of make_data_loader (src/data.py:76)
+        if 'train' in dataset:
+            d = device_csr(dataset['train'].data)
+            if _rng_mode() == 'reference':
+                E.index_batches(1, 1, False)
+                E.index_batches(1, 1, False)
+            base = torch.zeros(d.shape[1], device=dev)
+            count = torch.zeros(d.shape[1], device=dev)
+            native.base_fit(d.indices, d.data, base, count)
+            rl = d.row_len
+            imp_count = float(sum(int((rl[s:s + bs] > 0).sum()) for s in range(0, d.shape[0], bs)))
+            if implicit:
+                count = torch.full_like(count, imp_count)
+            self.model_state_dict[0] = {'base': base.cpu(), 'count': count.cpu()}
+            self._base = (base, count, imp_count)
+        else:
+            sd = self.model_state_dict[0]
+            base, count = sd['base'].to(dev), sd['count'].to(dev)
+            imp_count = float(count[0]) if implicit else 0.0
+        for k in dataset:
+            if k == 'test' and _rng_mode() == 'reference':
+                E.index_batches(1, 1, False)
+            t = device_csr(dataset[k].target)
+            pred = native.base_predict(base, count, t.indices, implicit, imp_count)
+            rows = np.repeat(np.arange(t.shape[0]), t.row_len)
+            cols = split[t.indices_host]
+            pred_h = pred.cpu().numpy()
+            output[k] = csr_matrix((pred_h, (rows, cols)), shape=_shape_target())
+            target[k] = csr_matrix((np.asarray(dataset[k].target.data), (rows, cols)), shape=_shape_target())
+            if k == 'train':
+                self._log_initialize(dataset[k], t, pred, metric, logger, bs)
+        return output, target
+
+    def _log_initialize(self, ds, t, pred, metric, logger, bs):
+        """Per-batch train metrics of the round-0 predictor, as the reference logs them (src/organization.py:46-66)."""
+        mode = cfg['data_mode']
+        d_len = np.diff(np.asarray(ds.data.indptr))
+        tgt = torch.from_numpy(np.asarray(ds.target.data, dtype=np.float32)).to(pred.device)
+        for s in range(0, t.shape[0], bs):
+            e = min(t.shape[0], s + bs)
+            n_in = int(d_len[s:e].sum())
+            lo, hi = int(t.indptr_host[s]), int(t.indptr_host[e])
+            if n_in == 0 or hi == lo:
+                continue
+            rows = torch.from_numpy(np.repeat(np.arange(s, e), t.row_len[s:e])).to(pred.device)
+            cols = t.indices[lo:hi].long()
+            inp = {'target_rating': tgt[lo:hi], 'target_' + mode: rows,
+                   'target_' + ('item' if mode == 'user' else 'user'): cols}
+            out = {'target_rating': pred[lo:hi]}
+            out['loss'] = models.loss_fn(out['target_rating'], inp['target_rating'])
+            logger.append(metric.evaluate(metric.metric_name['train'], inp, out), 'train', n_in)
+
+    # ------------------------------------------------------------------ local training
+    def _engine(self, data_m, target_m):
+        d = device_csr(data_m)
+        t = device_csr(target_m, with_values=False)
+        bs = cfg['local']['batch_size']['train']
+        enc, dec = cfg['ae']['encoder_hidden_size'], cfg['ae']['decoder_hidden_size']
+        if len(enc) != 2 or len(dec) != 2 or enc[0] != dec[1] or enc[1] != dec[0]:
+            raise NotImplementedError('the engine supports the reference AE shape [H1,H2]/[H2,H1] (src/utils.py:166-171)')
+        key = (id(d), id(t), bs)
+        if getattr(self, '_eng_key', None) != key:
+            if getattr(self, '_eng', None) is not None:
+                self._eng.close()
+            self._eng = E.OrgEngine(d, t, bs, enc[0], enc[1], native.LOSS_KIND[cfg['target_mode']])
+            self._eng_key = key
+            self._residual_buf = torch.empty(t.nnz, device=_device())
+        return self._eng, d, t
+
+    def train(self, dataset, metric, logger, iter):
+        """20 local Adam epochs of the AAE on the broadcast residuals (src/organization.py:140-178)."""
+        if self.model_name[iter] != 'ae':
+            raise TypeError("Organization.train only works with model 'ae' (as in the reference, SURVEY.md top item 1)")
+        eng, d, t = self._engine(dataset.data, dataset.target)
+        rng = _rng_mode()
+        dev = _device()
+        if rng == 'reference':
+            np.random.seed(cfg['seed'])  # side effect of make_data_loader (src/data.py:76)
+        num_users, num_items = dataset.num_users, dataset.num_items
+        model = models.ae(num_users['data'], num_items['data'], num_users['target'], num_items['target'])
+        flat0 = E.flat_from_state_dict(model.state_dict(), dev)
+        res = getattr(dataset.target, '_dmt_residual_dev', None)
+        if res is None:
+            res = torch.from_numpy(np.asarray(dataset.target.data, dtype=np.float32)).to(dev)
+        self._residual_buf.copy_(res)
+        eng.set_round(flat0, self._residual_buf)
+        hp = dict(lr=cfg['local']['lr'], betas=tuple(cfg['local']['betas']), weight_decay=cfg['local']['weight_decay'],
+                  max_norm=1.0)
+        n_epochs = cfg['local']['num_epochs']
+        bs = cfg['local']['batch_size']['train']
+        layouts = []
+        if rng == 'reference':
+            losses = []
+            for _ in range(n_epochs):
+                lay = E.EpochLayout(E.index_batches(d.shape[0], bs, True), eng.d_len, eng.t_len)
+                keep = [torch.empty(r, eng.H2).bernoulli_(0.5) if a else torch.zeros(r, eng.H2)
+                        for r, a in zip(lay.batch_rows, lay.active)]
+                keep = torch.cat(keep).to(torch.uint8).to(dev) if keep else None
+                lo = torch.zeros(len(lay.active), device=dev)
+                eng.enqueue_epoch(lay, keep=keep, hp=hp, loss_out=lo)
+                layouts.append(lay)
+                losses.append(lo)
+            loss_all = torch.cat(losses)
+        else:
+            for _ in range(n_epochs):
+                layouts.append(E.EpochLayout(E.fast_perm_batches(d.shape[0], bs), eng.d_len, eng.t_len))
+            loss_all = torch.zeros(sum(len(l.active) for l in layouts), device=dev)
+            seeds = [E.he_seed(cfg['seed'], self.organization_id, iter, e) for e in range(n_epochs)]
+            eng.enqueue_epochs(layouts, seeds, hp=hp, loss_out=loss_all)
+        flat = eng.params()
+        self._eng_params_iter = iter
+
+        def log():
+            vals = loss_all.cpu().tolist()
+            i = 0
+            for lay in layouts:
+                for a, n_in in zip(lay.active, lay.d_per_batch):
+                    if a:
+                        logger.append({metric.metric_name['train'][0]: vals[i]}, 'train', n=n_in)
+                    i += 1
+
+        sd = LazyStateDict(flat, eng, eng.n_enc, eng.n_dec, eng.H1, eng.H2, on_ready=log)
+        self.model_state_dict[iter] = sd
+        if 'dmt_sync' in cfg and cfg['dmt_sync']:
+            sd._force()
+        return
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, dataset, iter):
+        """Eval forward at every target position -> CSR with the sparsity of dataset.target (src/organization.py:180-217)."""
+        eng_data = device_csr(dataset.data)
+        t = device_csr(dataset.target, with_values=False)
+        if getattr(self, '_eng', None) is None:
+            self._engine(dataset.data, dataset.target)
+        eng = self._eng
+        dev = _device()
+        if _rng_mode() == 'reference':
+            np.random.seed(cfg['seed'])
+            nu, ni = dataset.num_users, dataset.num_items
+            models.ae(nu['data'], ni['data'], nu['target'], ni['target'])  # the reference builds (and inits) a model here
+            E.index_batches(1, 1, False)
+        sd = self.model_state_dict[iter]
+        if getattr(self, '_eng_params_iter', None) != iter:  # engine holds another round's parameters
+            flat = E.flat_from_state_dict(sd, dev)
+            eng.h.wait_current()
+            eng.h.set_params(flat)
+            self._eng_params_iter = iter
+        out = torch.empty(t.nnz, device=dev)
+        eng.predict(eng_data, t, out)
+        eng.h.signal_current()
+        pred = out.cpu().numpy()
+        if isinstance(sd, LazyStateDict):
+            sd._force()
+        m = csr_matrix((pred, t.indices_host.astype(np.int32, copy=False), t.indptr_host.astype(np.int32, copy=False)),
+                       shape=_shape_target(), copy=False)
+        m._dmt_pred_dev = out
+        return m

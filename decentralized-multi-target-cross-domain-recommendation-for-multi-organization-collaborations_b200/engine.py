@@ -1,0 +1,326 @@
+"""Device-resident MTAL engine: the data layout in HBM and the host-side sequencing of one assistance round.
+
+Layout (per rank):
+  * one canonical global CSR per split (rows = aligned entity, columns = ALL items/users): ``indptr``/``indices``
+    int32 + the ground truth ``y`` fp32; every per-entry vector of the round (F_t, residual, each organization's
+    prediction) is a plain fp32 array aligned with that CSR's storage order — the positional contract the
+    reference relies on (src/assist.py:45-46,94-117).
+  * ``O[split]``: [K x nnz] organization-major matrix of the K organizations' predictions (the payload of the
+    per-round exchange; rows of other ranks arrive by allgather).
+  * per organization: its data column block as CSR (local column ids) + an ``native.Org`` handle that owns the
+    parameters, Adam moments, activations, epoch plan and the captured per-epoch CUDA graph.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from . import native
+
+
+class DeviceCSR:
+    """CSR on the device (int32 indices) with a host copy of indptr for sizing decisions."""
+
+    def __init__(self, m, device="cuda", with_values=True):
+        m = m.tocsr()
+        if m.nnz >= 2 ** 31 - 2:
+            raise ValueError("nnz must fit int32")
+        self.shape = m.shape
+        self.nnz = int(m.nnz)
+        self.indptr_host = np.asarray(m.indptr, dtype=np.int64)
+        self.indices_host = np.asarray(m.indices)
+        self.indptr = torch.from_numpy(self.indptr_host.astype(np.int32)).to(device)
+        self.indices = torch.from_numpy(self.indices_host.astype(np.int32)).to(device)
+        self.data = torch.from_numpy(np.asarray(m.data, dtype=np.float32)).to(device) if with_values else None
+
+    @property
+    def row_len(self):
+        return np.diff(self.indptr_host)
+
+    def triple(self):
+        return (self.indptr, self.indices, self.data)
+
+    def pair(self):
+        return (self.indptr, self.indices)
+
+
+def csr_key(m):
+    """Content key of a scipy CSR's structure (used to reuse device uploads across API calls)."""
+    return (m.shape, int(m.nnz), zlib.crc32(np.ascontiguousarray(m.indptr).view(np.uint8)),
+            zlib.crc32(np.ascontiguousarray(m.indices).view(np.uint8)))
+
+
+def index_batches(n, batch_size, shuffle):
+    """Row-id batches of one pass of the reference's DataLoader (src/data.py:68-81). A real DataLoader over
+    ``range(n)`` is iterated so that torch's global generator is consumed exactly as in the reference: one base-seed
+    draw per iterator plus the RandomSampler's seed draw when shuffling."""
+    return [np.asarray(b, dtype=np.int64) for b in DataLoader(range(n), batch_size=batch_size, shuffle=shuffle,
+                                                              collate_fn=lambda x: x)]
+
+
+def fast_perm_batches(n, batch_size, generator=None):
+    """Shuffled row-id batches without the DataLoader machinery (production mode)."""
+    perm = torch.randperm(n, generator=generator).numpy()
+    return [perm[s:s + batch_size] for s in range(0, n, batch_size)]
+
+
+class EpochLayout:
+    """Host-side description of one local epoch for ``dmt_org_train_epoch``: per batch the sorted row ids with
+    entries (the reference's ``total_user``, src/models/ae.py:101), offsets, entry totals, and which batches carry
+    data (batches without data are skipped, src/organization.py:153-155)."""
+
+    def __init__(self, batches, d_len, t_len):
+        rows, off, active, b_rows = [], [0], [], []
+        for b in batches:
+            b = np.sort(np.asarray(b, dtype=np.int64))
+            b = b[(d_len[b] + t_len[b]) > 0]
+            rows.append(b)
+            off.append(off[-1] + len(b))
+            active.append(bool(d_len[b].sum() > 0))
+            b_rows.append(len(b))
+        self.rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+        self.row_off = np.asarray(off, dtype=np.int32)
+        self.active = active
+        self.batch_rows = b_rows
+        self.n_t = int(t_len[self.rows].sum())
+        self.n_d = int(d_len[self.rows].sum())
+        self.d_per_batch = [int(d_len[r].sum()) for r in rows]
+
+
+def flat_from_state_dict(sd, device):
+    """Reference AE state_dict -> the engine's flat layout W1t b1 W2 b2 W3 b3 W4 b4 (include/dmt_b200.h)."""
+    g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    return torch.cat([g("encoder_linear.weight").t().contiguous().view(-1), g("encoder_linear.bias"),
+                      g("encoder.blocks.0.weight").reshape(-1), g("encoder.blocks.0.bias"),
+                      g("decoder.blocks.0.weight").reshape(-1), g("decoder.blocks.0.bias"),
+                      g("decoder_linear.weight").reshape(-1), g("decoder_linear.bias")]).contiguous()
+
+
+def state_dict_from_flat(flat, n_enc, n_dec, H1=256, H2=128):
+    """Inverse of :func:`flat_from_state_dict`; returns tensors on the flat buffer's device."""
+    out, o = {}, 0
+
+    def take(n, shape):
+        nonlocal o
+        t = flat[o:o + n].view(shape)
+        o += n
+        return t
+
+    w1t = take(n_enc * H1, (n_enc, H1))
+    out["encoder.blocks.0.weight"] = None  # placeholder to keep the reference's key order
+    out["encoder.blocks.0.bias"] = None
+    out["decoder.blocks.0.weight"] = None
+    out["decoder.blocks.0.bias"] = None
+    out["encoder_linear.weight"] = w1t.t().contiguous()
+    out["encoder_linear.bias"] = take(H1, (H1,)).clone()
+    out["encoder.blocks.0.weight"] = take(H2 * H1, (H2, H1)).clone()
+    out["encoder.blocks.0.bias"] = take(H2, (H2,)).clone()
+    out["decoder.blocks.0.weight"] = take(H1 * H2, (H1, H2)).clone()
+    out["decoder.blocks.0.bias"] = take(H1, (H1,)).clone()
+    out["decoder_linear.weight"] = take(n_dec * H1, (n_dec, H1)).clone()
+    out["decoder_linear.bias"] = take(n_dec, (n_dec,)).clone()
+    return out
+
+
+class OrgEngine:
+    """One organization's AAE on the device (Organization.train / predict, reference src/organization.py:140-217)."""
+
+    def __init__(self, data: DeviceCSR, target: DeviceCSR, batch_rows, H1=256, H2=128, loss_kind=0):
+        self.data, self.target = data, target
+        self.n_rows, self.n_enc = data.shape
+        self.n_dec = target.shape[1]
+        self.H1, self.H2 = H1, H2
+        self.batch_rows = batch_rows
+        self.h = native.Org(self.n_rows, self.n_enc, self.n_dec, H1, H2, data.triple(), target.pair(), batch_rows,
+                            loss_kind)
+        self.d_len, self.t_len = data.row_len, target.row_len
+        self.device = data.indptr.device
+        self._keep_alive = []
+
+    def set_round(self, params_flat, residual):
+        """Fresh model + optimizer for the round (src/organization.py:144-148) and this round's targets."""
+        self.h.wait_current()
+        self.h.set_params(params_flat)
+        self.h.set_target(residual)
+        self._keep_alive = [params_flat, residual]
+
+    def enqueue_epoch(self, layout: EpochLayout, keep=None, seed=0, hp=None, loss_out=None):
+        rows = torch.from_numpy(layout.rows.astype(np.int32)).to(self.device)
+        off = torch.from_numpy(layout.row_off).to(self.device)
+        self.h.wait_current()
+        self.h.train_epoch(rows, off, layout.n_t, layout.n_d, keep=keep, seed=seed, epoch_loss=loss_out, **(hp or {}))
+        self._keep_alive += [rows, off, keep, loss_out]
+
+    def enqueue_epochs(self, layouts, seeds, hp=None, loss_out=None):
+        """Several epochs with ONE host->device copy of all their row lists (device-generated dropout)."""
+        nb = [len(l.row_off) - 1 for l in layouts]
+        rows_all = torch.from_numpy(np.concatenate([l.rows for l in layouts]).astype(np.int32)).to(self.device)
+        off_all = torch.from_numpy(np.concatenate([l.row_off for l in layouts])).to(self.device)
+        self.h.wait_current()
+        r0 = o0 = l0 = 0
+        for e, l in enumerate(layouts):
+            rows = rows_all[r0:r0 + len(l.rows)]
+            off = off_all[o0:o0 + nb[e] + 1]
+            lo = loss_out[l0:l0 + nb[e]] if loss_out is not None else None
+            self.h.train_epoch(rows, off, l.n_t, l.n_d, keep=None, seed=int(seeds[e]), epoch_loss=lo, **(hp or {}))
+            r0 += len(l.rows)
+            o0 += nb[e] + 1
+            l0 += nb[e]
+        self._keep_alive += [rows_all, off_all, loss_out]
+
+    def params(self):
+        return self.h.get_params()
+
+    def predict(self, data: DeviceCSR, target: DeviceCSR, out):
+        self.h.wait_current()
+        self.h.predict(data.triple(), target.pair(), target.shape[0], out)
+        return out
+
+    def sync(self):
+        self.h.sync()
+        self._keep_alive = self._keep_alive[:2]
+
+    def close(self):
+        self.h.close()
+
+
+class MtalState:
+    """Global per-split state of the coordinator (Assist, reference src/assist.py:13-41) on the device."""
+
+    def __init__(self, y: dict, data_split, target_mode, device="cuda"):
+        self.splits = list(y)
+        self.y = {k: DeviceCSR(y[k], device) for k in y}
+        self.K = len(data_split)
+        self.n_cols = y[self.splits[0]].shape[1]
+        self.target_mode = target_mode
+        self.loss_kind = native.LOSS_KIND[target_mode]
+        self.device = device
+        owner = np.full(self.n_cols, -1, np.int32)
+        local = np.zeros(self.n_cols, np.int32)
+        self.split_sizes = []
+        for i, cols in enumerate(data_split):
+            cols = np.asarray(cols, dtype=np.int64)
+            owner[cols] = i
+            local[cols] = np.arange(len(cols), dtype=np.int32)
+            self.split_sizes.append(len(cols))
+        if (owner < 0).any():
+            raise ValueError("every column must belong to exactly one organization")
+        self.owner_host, self.local_host = owner, local
+        self.owner = torch.from_numpy(owner).to(device)
+        self.data_split = [np.asarray(c, dtype=np.int64) for c in data_split]
+        self.O = {k: torch.zeros(self.K, self.y[k].nnz, device=device) for k in y}
+        self._views = {}
+
+    def residual(self, F, split, clamp, out=None):
+        return native.residual(F, self.y[split].data, self.loss_kind, 1.0 if clamp else 0.0, out)
+
+    def owner_view(self, split, i):
+        """Static per-owner view for the fit: positions of the owner's entries sorted by local column (stable),
+        their rank in the original order, and the per-column segment offsets."""
+        key = (split, i)
+        if key not in self._views:
+            ind = self.y[split].indices_host
+            pos = np.flatnonzero(self.owner_host[ind] == i)
+            idx = self.local_host[ind[pos]]
+            order = np.argsort(idx, kind="stable")
+            seg_off = np.zeros(self.split_sizes[i] + 1, np.int32)
+            seg_off[1:] = np.cumsum(np.bincount(idx, minlength=self.split_sizes[i]))
+            dev = self.device
+            self._views[key] = {
+                "pos_host": pos,
+                "pos": torch.from_numpy(pos[order].astype(np.int32)).to(dev),
+                "rank": torch.from_numpy(order.astype(np.int32)).to(dev),
+                "seg_off": torch.from_numpy(seg_off).to(dev),
+                "n": len(pos),
+            }
+        return self._views[key]
+
+    def match_end(self, split, match_rate):
+        """Global CSR position from which an owner's entries are UNmatched (partial alignment: only the first
+        int(n * match_rate) entries of the owner's view see the other organizations, src/assist.py:95-103)."""
+        ends = []
+        for i in range(self.K):
+            pos = self.owner_view(split, i)["pos_host"]
+            n_match = int(len(pos) * match_rate)
+            ends.append(pos[n_match] if n_match < len(pos) else self.y[split].nnz)
+        return torch.tensor(ends, dtype=torch.int64, device=self.device)
+
+    def fit_owner(self, i, F_prev, ar, ar_mode, aw_mode, match_rate, lr=0.1, steps=10):
+        """L-BFGS fit of owner i's assisted learning rates / assistance weights on the train split
+        (src/assist.py:118-129). The two-loop recursion runs on tiny host vectors (torch.optim.LBFGS, as in the
+        reference); every closure evaluation is ONE fused loss+gradient kernel over the owner's [n_i x K] view."""
+        n_rate = self.split_sizes[i]
+        rate = torch.full((n_rate,), float(ar))
+        weight = torch.ones(self.K) / self.K
+        free = []
+        if ar_mode == "optim":
+            rate.requires_grad_(True)
+            free.append(rate)
+        if aw_mode == "optim":
+            weight.requires_grad_(True)
+            free.append(weight)
+        if not free:
+            return rate, weight
+        v = self.owner_view("train", i)
+        n_match = int(v["n"] * match_rate) if match_rate < 1 else v["n"]
+        h, t, V = native.assist_gather_view(F_prev, self.y["train"].data, self.O["train"], v["pos"], v["rank"], i,
+                                            n_match)
+        scratch = torch.empty(native.load().dmt_assist_scratch_floats(self.K), device=self.device)
+        opt = torch.optim.LBFGS(free, lr=lr)
+
+        def closure():
+            out = native.assist_loss_grad(h, t, V, v["seg_off"], rate.detach().to(self.device),
+                                          weight.detach().to(self.device), self.loss_kind, scratch).cpu()
+            if rate.requires_grad:
+                rate.grad = out[1:1 + n_rate].clone()
+            if weight.requires_grad:
+                weight.grad = out[1 + n_rate:].clone()
+            return out[0]
+
+        for _ in range(steps):
+            opt.step(closure)
+        return rate.detach(), weight.detach()
+
+    def update(self, F_prev: dict, ar, ar_mode="constant", aw_mode="constant", match_rate=1.0, out=None):
+        """Assist.update (src/assist.py:81-179): fit per owner on train, then ONE combine pass per split."""
+        fitted = [self.fit_owner(i, F_prev["train"], ar, ar_mode, aw_mode, match_rate) for i in range(self.K)]
+        rate_col = np.zeros(self.n_cols, np.float32)
+        S = np.zeros((self.K, self.K), np.float32)
+        for i, (rate, weight) in enumerate(fitted):
+            rate_col[self.data_split[i]] = rate.numpy()
+            S[i] = torch.softmax(weight, -1).numpy()
+        rate_col_d = torch.from_numpy(rate_col).to(self.device)
+        S_d = torch.from_numpy(S).to(self.device)
+        F_next = {}
+        for k in self.splits:
+            me = self.match_end(k, match_rate) if match_rate < 1 else None
+            F_next[k] = native.assist_combine(F_prev[k], self.O[k], self.y[k].indices, self.owner, rate_col_d, S_d, me,
+                                              out[k] if out is not None else None)
+        return F_next, fitted
+
+
+def he_seed(seed, *parts):
+    """Deterministic 64-bit seed for the on-device dropout generator."""
+    x = (int(seed) * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+    for p in parts:
+        x = ((x ^ (int(p) + 0x632BE59BD9B4E019)) * 0xD6E8FEB86659FD93) & (2 ** 64 - 1)
+    return x
+
+
+def bytes_per_round(K, nnz_train, nnz_test, n_rows, n_enc_list, n_dec, epochs, batch_rows, H1=256, H2=128):
+    """Algorithmic (compulsory) bytes of one assist round, per SURVEY.md §8d: decoder SDDMM 4*H1+16 B per target
+    visit forward+first-backward, segmented dW4 4*H1+8 per target, dense Adam 28 B/param/step, residual 12 B and
+    combine (4K+12) B per rating."""
+    steps = epochs * math.ceil(n_rows / batch_rows)
+    total = 0
+    for n_enc in n_enc_list:
+        n_params = n_enc * H1 + H1 + H2 * H1 + H2 + H1 * H2 + H1 + n_dec * H1 + n_dec
+        total += epochs * nnz_train * ((4 * H1 + 16) + (4 * H1 + 8))  # decoder fwd/dZ3 + dW4 reduction
+        total += steps * n_params * (28 + 8)  # Adam + gradient zero/norm pass
+        total += (nnz_train + nnz_test) * (4 * H1 + 12)  # predict
+    total += (nnz_train + nnz_test) * (12 + 4 * K + 12)
+    return total

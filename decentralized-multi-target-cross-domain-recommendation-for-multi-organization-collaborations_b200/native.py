@@ -70,7 +70,7 @@ def _declare(lib):
         "dmt_dense_bwd_x": (I, [P, P, P, P, F, P, I, I, I, I, P]),
         "dmt_dense_bwd_w": (I, [P, P, P, P, I, I, I, P]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
-        "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
+        "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, I, P]),
         "dmt_org_create": (I, [C.POINTER(P), I, I, I, I, I, P, P, P, L, P, P, L, I, I, P]),
         "dmt_org_destroy": (I, [P]),
         "dmt_org_num_params": (L, [P]),
@@ -293,7 +293,7 @@ def ae_encoder_fwd(rows, indptr, indices, val, W1t, b1):
     return A1
 
 
-def ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, loss_kind, nnz, train):
+def ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, loss_kind, nnz, train, tanh_deriv=True):
     """pred is aligned with the target CSR (length nnz). Train mode also returns gout (same alignment),
     dZ3 [rows x H] and the per-row loss sums."""
     dev = A3.device
@@ -309,7 +309,7 @@ def ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, loss_kind, nnz, tr
         n_t = (ip[r + 1] - ip[r]).sum().to(torch.int32).reshape(1)
     check(load().dmt_ae_decoder_fwd(ptr(rows), rows.numel(), ptr(indptr), ptr(indices), ptr(target), ptr(A3), ptr(W4),
                                     ptr(b4), H, loss_kind, ptr(n_t), ptr(pred), ptr(gout), ptr(dz3), ptr(loss_rows),
-                                    stream()), "dmt_ae_decoder_fwd")
+                                    int(bool(tanh_deriv)), stream()), "dmt_ae_decoder_fwd")
     return pred, gout, dz3, loss_rows, n_t
 
 

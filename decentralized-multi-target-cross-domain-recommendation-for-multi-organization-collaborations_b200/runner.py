@@ -1,0 +1,185 @@
+"""Standalone experiment loop over the drop-in API (what reference src/train_recsys_assist.py:40-93 does), used by
+the GPU parity tests, smoke() and bench.py's end-to-end leg on boxes where the reference's drivers do not exist.
+
+It builds dataset objects with the attribute surface the hot path reads (``.data`` / ``.target`` scipy CSR,
+``.num_users`` / ``.num_items``, ``.transform.transforms[0]``, ``.item_attr`` / ``.user_profile``), splits the
+columns into organizations like src/data.py:200-274, and drives ``Assist`` / ``Organization`` exactly in the
+reference's order so that, in ``dmt_rng='reference'`` mode, torch's generator is consumed identically.
+"""
+import copy
+import types
+
+import numpy as np
+import torch
+
+from . import use_dropin
+from .config import cfg, make_cfg
+from .metrics import Logger, Metric
+
+
+class SplitDataset:
+    """One split ('train' / 'test') in the orientation of cfg['data_mode'] (rows = aligned entity)."""
+
+    def __init__(self, data, target, data_mode, item_attr=None, user_profile=None):
+        self.data, self.target, self.data_mode = data, target, data_mode
+        if item_attr is not None:
+            self.item_attr = {'data': item_attr, 'target': item_attr}
+        if user_profile is not None:
+            self.user_profile = {'data': user_profile, 'target': user_profile}
+        sizes = types.SimpleNamespace(num_users=self.num_users, num_items=self.num_items)
+        self.transform = types.SimpleNamespace(transforms=[sizes])
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    def _sizes(self, axis_rows):
+        a = 0 if axis_rows else 1
+        return {'data': self.data.shape[a], 'target': self.target.shape[a]}
+
+    @property
+    def num_users(self):
+        return self._sizes(self.data_mode == 'user')
+
+    @property
+    def num_items(self):
+        return self._sizes(self.data_mode == 'item')
+
+
+def fetch_dataset(data):
+    """{'train','test'} like the reference's datasets: test 'data' is the train matrix (src/datasets/movielens.py:367-371)."""
+    (trd, trt), (ted, tet) = data.split(cfg['target_mode'])
+    mats = {'train': (trd, trt), 'test': (ted, tet)}
+    if cfg['data_mode'] == 'item':
+        mats = {k: (a.T.tocsr(), b.T.tocsr()) for k, (a, b) in mats.items()}
+    out = {}
+    for k, (a, b) in mats.items():
+        a.sort_indices()
+        b.sort_indices()
+        out[k] = SplitDataset(a, b, cfg['data_mode'], data.item_attr, data.user_profile)
+    return out
+
+
+def process_dataset(dataset):
+    cfg['data_size'] = {'train': len(dataset['train']), 'test': len(dataset['test'])}
+    cfg['num_users'], cfg['num_items'] = dataset['train'].num_users, dataset['train'].num_items
+    cfg['info_size'] = None  # side information (info=1) is not wired into the engine path
+
+
+def split_dataset(dataset):
+    """Column split into organizations (src/data.py:200-242): 'genre' = one multinomial draw per column over its
+    genre indicator, redrawn until every organization is non-empty in all four matrices; 'random-K' = randperm chunks."""
+    K = cfg['num_organizations']
+    mode = cfg['data_split_mode']
+    if 'genre' in mode:
+        if cfg['data_mode'] != 'user':
+            raise NotImplementedError
+        attr = torch.tensor(dataset['train'].item_attr['data'])
+        attr[attr.sum(-1) == 0] = 1
+        while True:
+            idx = torch.multinomial(attr, 1).view(-1).numpy()
+            split = [np.where(idx == i)[0] for i in range(K)]
+            mats = [dataset[k].data for k in ('train', 'test')] + [dataset[k].target for k in ('train', 'test')]
+            if all(len(s) > 0 and all(m[:, s].nnz > 0 for m in mats) for s in split):
+                return [torch.tensor(s) for s in split]
+    if 'random' in mode:
+        n = dataset['train'].data.shape[1]
+        chunks = list(torch.randperm(n).split(n // K))
+        return chunks[:K - 1] + [torch.cat(chunks[K - 1:])]
+    raise ValueError('Not valid data split mode')
+
+
+def make_split_dataset(dataset, data_split):
+    out = []
+    for s in data_split:
+        cols = s.numpy()
+        out.append({k: SplitDataset(dataset[k].data[:, cols].tocsr(), dataset[k].target[:, cols].tocsr(),
+                                    cfg['data_mode']) for k in dataset})
+    return out
+
+
+def initialize(dataset, assist, organization, metric, logger):
+    """Round 0: every organization's base predictor, assembled into the global output / target matrices
+    (src/train_recsys_assist.py:98-141)."""
+    from scipy.sparse import csr_matrix
+
+    parts = {k: {'o': [], 't': []} for k in dataset[0]}
+    for i in range(len(dataset)):
+        out_i, tgt_i = organization[i].initialize(dataset[i], metric, logger, 0)
+        for k in dataset[0]:
+            parts[k]['o'].append(out_i[k].tocoo())
+            parts[k]['t'].append(tgt_i[k].tocoo())
+    shape = (cfg['num_users']['target'], cfg['num_items']['target']) if cfg['data_mode'] == 'user' else \
+        (cfg['num_items']['target'], cfg['num_users']['target'])
+    for k in dataset[0]:
+        for name, store in (('o', assist.organization_output), ('t', assist.organization_target)):
+            coo = parts[k][name]
+            store[0][k] = csr_matrix((np.concatenate([c.data for c in coo]),
+                                      (np.concatenate([c.row for c in coo]), np.concatenate([c.col for c in coo]))),
+                                     shape=shape)
+    logger.safe(False)
+    logger.reset()
+
+
+def evaluate(assist, metric, logger, epoch):
+    """Global test metrics in row blocks of the test batch size (src/train_recsys_assist.py:175-217)."""
+    import models
+
+    F = assist.organization_output[epoch]['test']
+    y = assist.organization_target[0]['test']
+    bs = cfg[cfg['model_name']]['batch_size']['test']
+    mode = cfg['data_mode']
+    for s in range(0, F.shape[0], bs):
+        lo, hi = y.indptr[s], y.indptr[min(F.shape[0], s + bs)]
+        if hi == lo:
+            continue
+        rows = torch.from_numpy(np.repeat(np.arange(s, min(F.shape[0], s + bs)),
+                                          np.diff(y.indptr[s:min(F.shape[0], s + bs) + 1])).astype(np.int64))
+        cols = torch.from_numpy(y.indices[lo:hi].astype(np.int64))
+        out = {'target_rating': torch.from_numpy(F.data[lo:hi])}
+        inp = {'target_rating': torch.from_numpy(y.data[lo:hi]), 'target_' + mode: rows,
+               'target_' + ('item' if mode == 'user' else 'user'): cols}
+        out['loss'] = models.loss_fn(out['target_rating'], inp['target_rating'])
+        logger.append(metric.evaluate(metric.metric_name['test'], inp, out), 'test', n=int(hi - lo))
+    return {k: float(v) for k, v in logger.mean.items() if k.startswith('test/')}
+
+
+def run_assist_experiment(data, control_name, seed=0, local_epochs=None, rounds=None, rng='device', keep_objects=False,
+                          on_round=None):
+    """Whole MTAL experiment through the drop-in API. Returns per-round global outputs and test metrics."""
+    make_cfg(control_name, device='cuda', seed=seed)
+    cfg['dmt_rng'] = rng
+    if local_epochs is not None:
+        cfg['local']['num_epochs'] = local_epochs
+    if rounds is not None:
+        cfg['global']['num_epochs'] = rounds
+    models, organization_mod, assist_mod = use_dropin()
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed(seed)
+    dataset = fetch_dataset(data)
+    process_dataset(dataset)
+    data_split = split_dataset(dataset)
+    dataset = make_split_dataset(dataset, data_split)
+    assist = assist_mod.Assist(data_split)
+    organization = assist.make_organization()
+    names = ['Loss', 'RMSE'] if cfg['target_mode'] == 'explicit' else ['Loss', 'NDCG']
+    metric = Metric({'train': names, 'test': names})
+    logger = Logger()
+    initialize(dataset, assist, organization, metric, logger)
+    metrics = {0: evaluate(assist, metric, logger, 0)}
+    logger.reset()
+    for t in range(1, cfg['global']['num_epochs'] + 1):
+        dataset = assist.make_dataset(dataset, t)
+        for i in range(len(organization)):
+            organization[i].train(dataset[i]['train'], metric, logger, t)
+        outs = [{k: organization[i].predict(dataset[i][k], t) for k in dataset[i]} for i in range(len(dataset))]
+        assist.update(outs, t)
+        metrics[t] = evaluate(assist, metric, logger, t)
+        logger.reset()
+        if on_round is not None:
+            on_round(t)
+    res = {'F': [{k: m[k].data.copy() for k in m} for m in assist.organization_output], 'metrics': metrics,
+           'data_split': [s.numpy() for s in data_split], 'y': assist.organization_target[0],
+           'ar_state_dict': assist.ar_state_dict}
+    if keep_objects:
+        res.update(assist=assist, organization=organization, dataset=dataset)
+    return res

@@ -149,11 +149,12 @@ int dmt_ae_encoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, c
                        const float* val, const float* W1t, const float* b1, int H, float* A1, void* stream);
 /* Decoder last layer + loss + first backward product in one pass over the target rows (src/models/ae.py:135-142,153-156):
  * for each target entry e (CSR position) of batch row j: o = A3[j].W4[c_e] + b4[c_e]; pred[e] = o (pred may be NULL);
- * train mode (gout != NULL): gout[e] = dloss/do / *n_targets, dZ3[j] = (sum_e gout[e] W4[c_e]) * (1 - A3[j]^2),
- * loss_rows[j] = sum_e loss. H in {128,256,384,512}. */
+ * train mode (gout != NULL): gout[e] = dloss/do / *n_targets, dZ3[j] = (sum_e gout[e] W4[c_e]) [* (1 - A3[j]^2) when
+ * tanh_deriv != 0: A3 is the tanh output of the last decoder block], loss_rows[j] = sum_e loss. H in {128,256,384,512}. */
 int dmt_ae_decoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices,
                        const float* target, const float* A3, const float* W4, const float* b4, int H, int loss_kind,
-                       const int32_t* n_targets, float* pred, float* gout, float* dZ3, float* loss_rows, void* stream);
+                       const int32_t* n_targets, float* pred, float* gout, float* dZ3, float* loss_rows, int tanh_deriv,
+                       void* stream);
 
 /* ------------------------------------------------------------------ device-resident organization engine */
 

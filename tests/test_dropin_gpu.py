@@ -1,0 +1,148 @@
+"""Drop-in API (models / Organization / Assist) on the GPU against the reference's golden vectors.
+
+module level : same state_dict + same batch (+ same dropout draw) -> same target_rating, loss, .grad
+round level  : same seed, RNG-identical replay ('dmt_rng' = 'reference') -> same organization_output[t] and the
+               same test metrics after every round (RMSE / NDCG within 1e-4, BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_io import Fixture, cases, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import dmtcdr_b200
+
+    return dmtcdr_b200.use_dropin()
+
+
+def set_cfg(fx):
+    from dmtcdr_b200.config import make_cfg, cfg
+
+    make_cfg(fx.meta["control_name"], device="cuda", seed=0)
+    cfg["info_size"] = fx.meta["info_size"]
+    cfg["num_users"], cfg["num_items"] = fx.meta["num_users"], fx.meta["num_items"]
+    return cfg
+
+
+MODULE_CASES = [c for c in cases("model") if "_mf_" in c or "_ae_" in c]
+
+
+@pytest.mark.parametrize("case", MODULE_CASES)
+def test_module_forward_backward(dropin, case):
+    models, _, _ = dropin
+    fx = Fixture(case)
+    cfg = set_cfg(fx)
+    m = fx.meta
+    if m["model_name"] == "ae":
+        model = models.ae(m["enc_users"], m["enc_items"], m["dec_users"], m["dec_items"])
+    else:
+        model = models.mf(m["n_users"], m["n_items"])
+    model.load_state_dict(fx.group("sd0"))
+    model = model.cuda()
+    for j in (0, 1):
+        b = {k: v.cuda() for k, v in fx.group("b{}/in".format(j)).items() if k != "local"}
+        model.train(True)
+        model.zero_grad()
+        if m["model_name"] == "ae":
+            b["local"] = True
+            model.keep_override = torch.from_numpy(fx["b{}/mask".format(j)])
+        out = model(b)
+        out["loss"].backward()
+        assert rel_err(out["target_rating"].detach().cpu(), fx["b{}/train/target_rating".format(j)]) < 2e-5
+        ref_loss = float(fx["b{}/train/loss".format(j)])
+        assert abs(float(out["loss"]) - ref_loss) <= 1e-5 * abs(ref_loss)
+        for name, p in model.named_parameters():
+            ref = fx["b{}/grad/{}".format(j, name)]
+            got = np.zeros_like(ref) if p.grad is None else p.grad.cpu().numpy()
+            assert rel_err(got, ref) < 5e-5 or np.abs(got - ref).max() < 1e-9, name
+        model.train(False)
+        with torch.no_grad():
+            if m["model_name"] == "ae":
+                b["local"] = False
+            out = model(b)
+        assert rel_err(out["target_rating"].cpu(), fx["b{}/eval/target_rating".format(j)]) < 2e-5
+        ref_loss = float(fx["b{}/eval/loss".format(j)])
+        assert abs(float(out["loss"]) - ref_loss) <= 1e-5 * abs(ref_loss)
+
+
+@pytest.mark.parametrize("case", MODULE_CASES)
+def test_module_with_torch_optimizer(dropin, case):
+    """The drivers own clip_grad_norm_ + torch.optim.Adam for these models (src/train_recsys_joint.py:129-134)."""
+    models, _, _ = dropin
+    fx = Fixture(case)
+    set_cfg(fx)
+    m = fx.meta
+    if m["model_name"] == "ae":
+        model = models.ae(m["enc_users"], m["enc_items"], m["dec_users"], m["dec_items"])
+    else:
+        model = models.mf(m["n_users"], m["n_items"])
+    model.load_state_dict(fx.group("sd0"))
+    model = model.cuda()
+    model.train(True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=5e-4)
+    losses = []
+    for step in range(4):
+        b = {k: v.cuda() for k, v in fx.group("b{}/in".format(step % 2)).items() if k != "local"}
+        if m["model_name"] == "ae":
+            b["local"] = True
+            model.keep_override = torch.from_numpy(fx["steps/mask{}".format(step)])
+        opt.zero_grad()
+        out = model(b)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
+        opt.step()
+        losses.append(float(out["loss"]))
+    assert rel_err(losses, fx["steps/loss"]) < 1e-5
+    for name, ref in fx.group("sd4", as_torch=False).items():
+        assert rel_err(model.state_dict()[name].cpu().numpy(), ref) < 5e-4, name
+
+
+@pytest.mark.parametrize("case", cases("round"))
+def test_round_replay_vs_reference(dropin, case):
+    from dmtcdr_b200 import runner, synth
+
+    fx = Fixture(case)
+    m = fx.meta
+    data = synth.make_rating_data("tiny-" + m["data_name"], seed=0)
+    res = runner.run_assist_experiment(data, m["control_name"], seed=0, local_epochs=m["local_epochs"],
+                                       rounds=m["rounds"], rng="reference", keep_objects=True)
+    K = m["num_organizations"]
+    for i in range(K):
+        assert np.array_equal(res["data_split"][i], fx["data_split/{}".format(i)])
+    for k in ("train", "test"):
+        assert np.array_equal(res["y"][k].indices, fx["y/{}/indices".format(k)])  # bit-exact structure
+        assert rel_err(res["F"][0][k], fx["F0/{}/data".format(k)]) < 1e-6
+    sd = res["organization"][0].model_state_dict[1]
+    for name, ref in fx.group("org0_sd1", as_torch=False).items():
+        assert rel_err(sd[name].numpy(), ref) < 5e-4, name
+    for t in (1, 2):
+        for k in ("train", "test"):
+            assert rel_err(res["F"][t][k], fx["F{}/{}".format(t, k)]) < 5e-4, (t, k)
+        for i in range(K):
+            a = res["ar_state_dict"][t][i]
+            assert rel_err(a["assist_rate"], fx["ar{}/rate/{}".format(t, i)]) < 2e-3
+            assert rel_err(a["assist_weight"], fx["ar{}/weight/{}".format(t, i)]) < 2e-3
+    gm = fx.json("metrics")
+    for t in (0, 1, 2):
+        for name, ref in gm[str(t)].items():
+            assert abs(res["metrics"][t][name] - ref) <= 1e-4, (t, name, res["metrics"][t][name], ref)
+
+
+def test_cpu_tensors_fail_loudly(dropin):
+    """No CPU path: the models refuse host tensors instead of silently computing elsewhere."""
+    models, _, _ = dropin
+    from dmtcdr_b200 import native
+
+    fx = Fixture("model_mf_user_explicit")
+    set_cfg(fx)
+    model = models.mf(fx.meta["n_users"], fx.meta["n_items"])
+    b = dict(fx.group("b0/in"))
+    with pytest.raises(native.NativeError):
+        model(b)

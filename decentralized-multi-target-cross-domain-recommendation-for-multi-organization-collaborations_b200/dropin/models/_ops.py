@@ -92,7 +92,7 @@ class SparseDecoderLossFn(torch.autograd.Function):
         _need_cuda(A3, weight)
         n_rows = indptr.numel() - 1
         rows = torch.arange(n_rows, dtype=torch.int32, device=A3.device)
-        train = torch.is_grad_enabled() and (A3.requires_grad or weight.requires_grad)
+        train = any(ctx.needs_input_grad[:3])  # grad mode is off inside forward(); this is the reliable signal
         ctx.set_materialize_grads(False)
         A3c, Wc, bc = A3.contiguous(), weight.contiguous(), bias.contiguous()
         nnz = indices.numel()
@@ -131,7 +131,7 @@ class MFFn(torch.autograd.Function):
         bu_, bi_ = bu.reshape(-1).contiguous(), bi.reshape(-1).contiguous()
         pu_ = pu.contiguous() if pu is not None else None
         pi_ = pi.contiguous() if pi is not None else None
-        train = torch.is_grad_enabled()
+        train = any(ctx.needs_input_grad)
         pred, dpred, sums = native.mf_fwd(user, item, rating, Wu_, Wi_, bu_, bi_, bias.contiguous(), loss_kind, pu_,
                                           pi_, want_grad=train)
         n = user.numel()

@@ -26,7 +26,14 @@ void set_error(const char* msg);
         }                          \
     } while (0)
 
-#define DMT_LAUNCH_CHECK() DMT_CUDA(cudaGetLastError())
+void count_launch(long long n);
+long long launch_count();
+
+#define DMT_LAUNCH_CHECK()              \
+    do {                                \
+        dmt::count_launch(1);           \
+        DMT_CUDA(cudaGetLastError());   \
+    } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

@@ -73,6 +73,7 @@ struct dmt_org {
     cudaEvent_t ev;
     // graph cache
     cudaGraphExec_t exec;
+    long long g_kernels;  // our kernel launches captured in the graph
     int g_nb, g_keep;
     AdamHyper g_hp;
 };
@@ -237,7 +238,9 @@ static int build_plan(dmt_org* o, int n, int nb, int64_t n_t, int64_t n_d) {
 }
 
 // ---------------------------------------------------------------- one training step (enqueue only)
-static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp) {
+enum StepClass { K_ENC = 0, K_DENSE_FWD, K_ZERO, K_DEC, K_SEG_W4, K_DENSE_BWD, K_SEG_W1, K_NORM, K_ADAM, K_NCLASS };
+
+static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only = -1) {
     cudaStream_t st = o->st;
     const int B = o->batch_rows, H1 = o->H1, H2 = o->H2;
     BatchRef br{o->row_off_buf, o->active, b, 0, 0};
@@ -245,6 +248,7 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp) {
     float *W3 = o->P + o->oW3, *b3 = o->P + o->ob3, *W4 = o->P + o->oW4, *b4 = o->P + o->ob4;
     float* G = o->G;
     int rc;
+#define WANT(cls) (only < 0 || only == (cls))
     // keep bytes of batch b start at row row_off[b]; the dense epilogue adds that base itself (replayable graph).
     Dropout drop;
     drop.keep = use_keep ? o->keep_buf : nullptr;
@@ -257,38 +261,53 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp) {
     drop.enabled = 1;
     Dropout nodrop;
     // forward
-    if ((rc = launch_ae_encoder_fwd(o->rows_buf, o->d_indptr, o->d_indices, o->d_val, W1t, b1, H1, o->a1, B, br, st)))
-        return rc;
-    if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, o->a2, drop, B, H2, H1, 1, br, st))) return rc;
-    if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, B, H1, H2, 1, br, st))) return rc;
-    DMT_CUDA(cudaMemsetAsync(G, 0, (size_t)o->n_params * sizeof(float), st));
+    if (WANT(K_ENC))
+        if ((rc = launch_ae_encoder_fwd(o->rows_buf, o->d_indptr, o->d_indices, o->d_val, W1t, b1, H1, o->a1, B, br,
+                                        st)))
+            return rc;
+    if (WANT(K_DENSE_FWD)) {
+        if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, o->a2, drop, B, H2, H1, 1, br, st))) return rc;
+        if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, B, H1, H2, 1, br, st))) return rc;
+    }
+    if (WANT(K_ZERO)) DMT_CUDA(cudaMemsetAsync(G, 0, (size_t)o->n_params * sizeof(float), st));
     // decoder + loss + dZ3
-    if ((rc = launch_ae_decoder_fwd(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1, DMT_LOSS_MSE,
-                                    o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, o->dz3, o->loss_rows, 1, B,
-                                    br, st)))
-        return rc;
+    if (WANT(K_DEC))
+        if ((rc = launch_ae_decoder_fwd(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1,
+                                        DMT_LOSS_MSE, o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, o->dz3,
+                                        o->loss_rows, 1, B, br, st)))
+            return rc;
     // dW4, db4: segmented over (batch, target column)
-    SegRef st4{o->pt.batch_seg_off, nullptr, b, 0, 0, o->n_dec};
-    if ((rc = launch_segment_reduce_rows(o->pt.perm, o->pt.seg_key, o->pt.seg_off, st4, o->n_dec, o->gbuf,
-                                         o->pt.ent_row, o->a3, H1, G + o->oW4, G + o->ob4, o->active, st)))
-        return rc;
+    if (WANT(K_SEG_W4)) {
+        SegRef st4{o->pt.batch_seg_off, nullptr, b, 0, 0, o->n_dec};
+        if ((rc = launch_segment_reduce_rows(o->pt.perm, o->pt.seg_key, o->pt.seg_off, st4, o->n_dec, o->gbuf,
+                                             o->pt.ent_row, o->a3, H1, G + o->oW4, G + o->ob4, o->active, st)))
+            return rc;
+    }
     // dense backward
-    if ((rc = launch_dense_bwd_w(o->dz3, o->c, G + o->oW3, G + o->ob3, B, H1, H2, br, st))) return rc;
-    if ((rc = launch_dense_bwd_x(o->dz3, W3, o->a2, drop, o->dz2, B, H1, H2, 1, br, st))) return rc;
-    if ((rc = launch_dense_bwd_w(o->dz2, o->a1, G + o->oW2, G + o->ob2, B, H2, H1, br, st))) return rc;
-    if ((rc = launch_dense_bwd_x(o->dz2, W2, o->a1, nodrop, o->dz1, B, H2, H1, 1, br, st))) return rc;
+    if (WANT(K_DENSE_BWD)) {
+        if ((rc = launch_dense_bwd_w(o->dz3, o->c, G + o->oW3, G + o->ob3, B, H1, H2, br, st))) return rc;
+        if ((rc = launch_dense_bwd_x(o->dz3, W3, o->a2, drop, o->dz2, B, H1, H2, 1, br, st))) return rc;
+        if ((rc = launch_dense_bwd_w(o->dz2, o->a1, G + o->oW2, G + o->ob2, B, H2, H1, br, st))) return rc;
+        if ((rc = launch_dense_bwd_x(o->dz2, W2, o->a1, nodrop, o->dz1, B, H2, H1, 1, br, st))) return rc;
+    }
     // dW1t: segmented over (batch, data column); db1 = column sums of dZ1
-    SegRef sd{o->pd.batch_seg_off, nullptr, b, 0, 0, o->n_enc};
-    if ((rc = launch_segment_reduce_rows(o->pd.perm, o->pd.seg_key, o->pd.seg_off, sd, o->n_enc, o->dval_ord,
-                                         o->pd.ent_row, o->dz1, H1, G + o->oW1, nullptr, o->active, st)))
-        return rc;
-    if ((rc = launch_colsum(o->dz1, H1, G + o->ob1, br, st))) return rc;
+    if (WANT(K_SEG_W1)) {
+        SegRef sd{o->pd.batch_seg_off, nullptr, b, 0, 0, o->n_enc};
+        if ((rc = launch_segment_reduce_rows(o->pd.perm, o->pd.seg_key, o->pd.seg_off, sd, o->n_enc, o->dval_ord,
+                                             o->pd.ent_row, o->dz1, H1, G + o->oW1, nullptr, o->active, st)))
+            return rc;
+        if ((rc = launch_colsum(o->dz1, H1, G + o->ob1, br, st))) return rc;
+    }
     // clip + Adam
-    if ((rc = launch_sqnorm_stage1(G, o->n_params, o->partial, br, st))) return rc;
-    if ((rc = launch_adam_prepare(o->partial, kNormBlocks, nullptr, nullptr, o->sc, hp, 0, o->step_dev, o->loss_rows,
-                                  o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
-        return rc;
-    if ((rc = launch_adam(o->P, G, o->M, o->V, o->n_params, o->sc, hp, st))) return rc;
+    if (WANT(K_NORM))
+        if ((rc = launch_sqnorm_stage1(G, o->n_params, o->partial, br, st))) return rc;
+    if (WANT(K_ADAM)) {
+        if ((rc = launch_adam_prepare(o->partial, kNormBlocks, nullptr, nullptr, o->sc, hp, 0, o->step_dev,
+                                      o->loss_rows, o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
+            return rc;
+        if ((rc = launch_adam(o->P, G, o->M, o->V, o->n_params, o->sc, hp, st))) return rc;
+    }
+#undef WANT
     return 0;
 }
 
@@ -450,7 +469,10 @@ int dmt_org_train_epoch(dmt_org_t* o, const int32_t* rows, const int32_t* row_of
         if (o->exec) { cudaGraphExecDestroy(o->exec); o->exec = nullptr; }
         cudaGraph_t graph = nullptr;
         DMT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        long long before = launch_count();
         for (int b = 0; b < n_batches && rc == 0; ++b) rc = enqueue_step(o, b, use_keep != 0, hp);
+        o->g_kernels = launch_count() - before;
+        count_launch(-o->g_kernels);  // captured, not executed: counted at every cudaGraphLaunch instead
         cudaError_t e = cudaStreamEndCapture(st, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
@@ -460,6 +482,7 @@ int dmt_org_train_epoch(dmt_org_t* o, const int32_t* rows, const int32_t* row_of
         o->g_nb = n_batches; o->g_keep = use_keep; o->g_hp = hp;
     }
     DMT_CUDA(cudaGraphLaunch(o->exec, st));
+    count_launch(o->g_kernels);
     if (epoch_loss)
         DMT_CUDA(cudaMemcpyAsync(epoch_loss, o->loss_buf, (size_t)n_batches * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -487,6 +510,50 @@ int dmt_org_predict(dmt_org_t* o, const int32_t* d_indptr, const int32_t* d_indi
             return rc;
     }
     return 0;
+}
+
+/* Average duration (ms) of every kernel class of one training step on batch b of the CURRENT plan (call after
+ * dmt_org_train_epoch): each class is launched `reps` times back to back between two CUDA events on the handle's
+ * stream. Parameters and optimizer state are restored afterwards. ms_out has dmt_org_profile_classes() entries:
+ * encoder, dense fwd (2 GEMMs), grad zero, decoder+loss+dZ3, dW4 segments, dense bwd (4 GEMMs + 2 col-sums),
+ * dW1 segments + col-sum, grad norm, Adam. */
+int dmt_org_profile_classes(void) { return K_NCLASS; }
+
+int dmt_org_profile_step(dmt_org_t* o, int b, int reps, float* ms_out) {
+    DMT_REQUIRE(o && ms_out && reps > 0 && b >= 0 && b < o->nb_cap, "dmt_org_profile_step: bad argument");
+    cudaStream_t st = o->st;
+    float *P0 = nullptr, *M0 = nullptr, *V0 = nullptr;
+    int step0 = 0;
+    size_t bytes = (size_t)o->n_params * 4;
+    DMT_CUDA(cudaMalloc(&P0, bytes)); DMT_CUDA(cudaMalloc(&M0, bytes)); DMT_CUDA(cudaMalloc(&V0, bytes));
+    DMT_CUDA(cudaMemcpyAsync(P0, o->P, bytes, cudaMemcpyDeviceToDevice, st));
+    DMT_CUDA(cudaMemcpyAsync(M0, o->M, bytes, cudaMemcpyDeviceToDevice, st));
+    DMT_CUDA(cudaMemcpyAsync(V0, o->V, bytes, cudaMemcpyDeviceToDevice, st));
+    DMT_CUDA(cudaMemcpyAsync(&step0, o->step_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    cudaEvent_t e0, e1;
+    DMT_CUDA(cudaEventCreate(&e0)); DMT_CUDA(cudaEventCreate(&e1));
+    AdamHyper hp = o->g_nb >= 0 ? o->g_hp : AdamHyper{1e-3, 0.9, 0.999, 1e-8, 5e-4, 1.f};
+    int rc = 0;
+    // one full step first so every buffer a class reads holds this batch's data
+    rc = enqueue_step(o, b, o->g_keep != 0, hp);
+    for (int cls = 0; cls < K_NCLASS && rc == 0; ++cls) {
+        rc = enqueue_step(o, b, o->g_keep != 0, hp, cls);  // warm
+        DMT_CUDA(cudaEventRecord(e0, st));
+        for (int r = 0; r < reps && rc == 0; ++r) rc = enqueue_step(o, b, o->g_keep != 0, hp, cls);
+        DMT_CUDA(cudaEventRecord(e1, st));
+        DMT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DMT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        ms_out[cls] = ms / reps;
+    }
+    cudaMemcpyAsync(o->P, P0, bytes, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(o->M, M0, bytes, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(o->V, V0, bytes, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(o->step_dev, &step0, sizeof(int), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(P0); cudaFree(M0); cudaFree(V0);
+    return rc;
 }
 
 int dmt_org_sync(dmt_org_t* o) {

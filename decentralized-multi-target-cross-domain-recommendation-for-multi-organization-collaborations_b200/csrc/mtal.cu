@@ -12,6 +12,11 @@ void set_error(const char* msg) {
     g_err[i] = 0;
 }
 
+// number of OUR kernels launched (captured launches are added when their graph is launched; engine.cu)
+static long long g_launches = 0;
+void count_launch(long long n) { __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAXED); }
+long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 // ---------------------------------------------------------------- residual (reference src/assist.py:45-58)
 __global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__ F, const float* __restrict__ y,
                                                        float* __restrict__ r, int64_t n, int kind, float clamp) {
@@ -251,6 +256,7 @@ extern "C" {
 
 const char* dmt_last_error(void) { return g_err; }
 int dmt_version(void) { return 100; }
+int64_t dmt_launch_count(void) { return (int64_t)launch_count(); }
 
 int dmt_check_device(void) {
     int dev = 0;

@@ -1,0 +1,61 @@
+"""Organization -> rank sharding and the per-round exchange of organization outputs.
+
+The reference passes the K prediction matrices around as Python lists inside one process
+(src/train_recsys_assist.py:166-172). Here rank r owns the contiguous block of organizations
+[r*c, (r+1)*c), c = ceil(K / world); after ``predict`` each rank holds its own rows of the organization-major
+matrix O[split] ([world*c x nnz], rows >= K are padding) and ONE in-place all-gather per split publishes the rest.
+NCCL over NVLink on the GPU box; gloo on CPU for the world_size-2 tests.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """torchrun-style init (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*). Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def org_block(K, world, rank):
+    """Organizations owned by ``rank``: a contiguous block of ceil(K/world) ids (possibly empty at the tail)."""
+    c = -(-K // world)
+    return list(range(rank * c, min(K, (rank + 1) * c))), c
+
+
+def exchange_outputs(O_full, chunk, rank, world, group=None):
+    """In-place all-gather of every split's organization-major matrix: rank r contributes rows [r*chunk, (r+1)*chunk)."""
+    if world == 1:
+        return
+    for k, O in O_full.items():
+        if O.shape[0] != chunk * world:
+            raise ValueError("O[{}] must have world*chunk rows for the in-place all-gather".format(k))
+        mine = O[rank * chunk:(rank + 1) * chunk]
+        dist.all_gather_into_tensor(O, mine, group=group)
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over ranks (device-timed numbers are reported as the max over ranks)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()

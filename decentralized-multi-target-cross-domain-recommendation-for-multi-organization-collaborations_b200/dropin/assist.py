@@ -62,7 +62,7 @@ class Assist:
             ref = st.y[split]
             if m.nnz != ref.nnz or not np.array_equal(m.indptr, ref.indptr_host):
                 raise ValueError('organization_output and organization_target must share one sparsity pattern')
-            self._F_dev[key] = torch.from_numpy(np.asarray(m.data, dtype=np.float32)).to(st.device)
+            self._F_dev[key] = E.to_dev(np.asarray(m.data, dtype=np.float32), st.device)
         return self._F_dev[key]
 
     # ------------------------------------------------------------------ make_dataset
@@ -74,10 +74,10 @@ class Assist:
             cfg['data_name'] == 'Douban' and cfg['data_mode'] == 'item' and cfg['target_mode'] == 'explicit')
         for k in dataset[0]:
             res_dev = st.residual(self._F(iter - 1, k), k, clamp)
-            res = res_dev.cpu().numpy()
+            res = E.to_host(res_dev).numpy()
             if 'pl' in cfg and cfg['pl'] != 'none':
                 res = make_privacy(res, cfg['pl_mode'], cfg['pl_param'])
-                res_dev = torch.from_numpy(res).to(st.device)
+                res_dev = E.to_dev(res, st.device)
             ref = st.y[k]
             if cfg['data_mode'] == 'user':
                 shape = (cfg['num_users']['target'], cfg['num_items']['target'])
@@ -118,7 +118,7 @@ class Assist:
                     raise ValueError('organization output {} does not match the target sparsity'.format(j))
                 dev_vals = getattr(m, '_dmt_pred_dev', None)
                 if dev_vals is None:
-                    dev_vals = torch.from_numpy(np.asarray(m.data, dtype=np.float32)).to(st.device)
+                    dev_vals = E.to_dev(np.asarray(m.data, dtype=np.float32), st.device)
                 st.O[k][j].copy_(dev_vals)
         a = cfg['assist']
         match_rate = a['match_rate'] if 'match_rate' in a else 1.0
@@ -136,5 +136,5 @@ class Assist:
             ref = st.y[k]
             self._F_dev[(iter, k)] = F
             self.organization_output[iter][k] = csr_matrix(
-                (F.cpu().numpy(), ref.indices_host.astype(np.int32), ref.indptr_host.astype(np.int32)), shape=shape)
+                (E.to_host(F).numpy(), ref.indices_host.astype(np.int32), ref.indptr_host.astype(np.int32)), shape=shape)
         return

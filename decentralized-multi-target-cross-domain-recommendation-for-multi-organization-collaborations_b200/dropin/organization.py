@@ -33,7 +33,7 @@ def device_csr(m, with_values=True):
         host = np.ascontiguousarray(m.data, dtype=np.float32)
         crc = E.zlib.crc32(host.view(np.uint8))
         if hit._values_crc != crc:
-            hit.data = torch.from_numpy(host).to(_device())
+            hit.data = E.to_dev(host, _device())
             hit._values_crc = crc
     return hit
 
@@ -74,7 +74,7 @@ class LazyStateDict(dict):
             flat, eng, n_enc, n_dec, H1, H2, on_ready = p
             eng.sync()
             sd = E.state_dict_from_flat(flat, n_enc, n_dec, H1, H2)
-            dict.update(self, {k: v.cpu() for k, v in sd.items()})
+            dict.update(self, {k: E.to_host(v) for k, v in sd.items()})
             if on_ready is not None:
                 on_ready()
         return self
@@ -157,7 +157,7 @@ class Organization:
             pred = native.base_predict(base, count, t.indices, implicit, imp_count)
             rows = np.repeat(np.arange(t.shape[0]), t.row_len)
             cols = split[t.indices_host]
-            pred_h = pred.cpu().numpy()
+            pred_h = E.to_host(pred).numpy()
             output[k] = csr_matrix((pred_h, (rows, cols)), shape=_shape_target())
             target[k] = csr_matrix((np.asarray(dataset[k].target.data), (rows, cols)), shape=_shape_target())
             if k == 'train':
@@ -214,7 +214,7 @@ class Organization:
         flat0 = E.flat_from_state_dict(model.state_dict(), dev)
         res = getattr(dataset.target, '_dmt_residual_dev', None)
         if res is None:
-            res = torch.from_numpy(np.asarray(dataset.target.data, dtype=np.float32)).to(dev)
+            res = E.to_dev(np.asarray(dataset.target.data, dtype=np.float32), dev)
         self._residual_buf.copy_(res)
         eng.set_round(flat0, self._residual_buf)
         hp = dict(lr=cfg['local']['lr'], betas=tuple(cfg['local']['betas']), weight_decay=cfg['local']['weight_decay'],
@@ -228,7 +228,7 @@ class Organization:
                 lay = E.EpochLayout(E.index_batches(d.shape[0], bs, True), eng.d_len, eng.t_len)
                 keep = [torch.empty(r, eng.H2).bernoulli_(0.5) if a else torch.zeros(r, eng.H2)
                         for r, a in zip(lay.batch_rows, lay.active)]
-                keep = torch.cat(keep).to(torch.uint8).to(dev) if keep else None
+                keep = E.to_dev(torch.cat(keep).to(torch.uint8), dev) if keep else None
                 lo = torch.zeros(len(lay.active), device=dev)
                 eng.enqueue_epoch(lay, keep=keep, hp=hp, loss_out=lo)
                 layouts.append(lay)
@@ -244,7 +244,7 @@ class Organization:
         self._eng_params_iter = iter
 
         def log():
-            vals = loss_all.cpu().tolist()
+            vals = E.to_host(loss_all).tolist()
             i = 0
             for lay in layouts:
                 for a, n_in in zip(lay.active, lay.d_per_batch):
@@ -281,7 +281,7 @@ class Organization:
         out = torch.empty(t.nnz, device=dev)
         eng.predict(eng_data, t, out)
         eng.h.signal_current()
-        pred = out.cpu().numpy()
+        pred = E.to_host(out).numpy()
         if isinstance(sd, LazyStateDict):
             sd._force()
         m = csr_matrix((pred, t.indices_host.astype(np.int32, copy=False), t.indptr_host.astype(np.int32, copy=False)),

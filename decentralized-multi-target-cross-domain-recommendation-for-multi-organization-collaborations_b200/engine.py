@@ -22,6 +22,20 @@ from torch.utils.data import DataLoader
 from . import native
 
 
+XFER = {"h2d": 0, "d2h": 0}  # bytes moved between host and device through this package (bench.py reads it)
+
+
+def to_dev(x, device):
+    t = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+    XFER["h2d"] += t.numel() * t.element_size()
+    return t.to(device)
+
+
+def to_host(t):
+    XFER["d2h"] += t.numel() * t.element_size()
+    return t.cpu()
+
+
 class DeviceCSR:
     """CSR on the device (int32 indices) with a host copy of indptr for sizing decisions."""
 
@@ -33,9 +47,9 @@ class DeviceCSR:
         self.nnz = int(m.nnz)
         self.indptr_host = np.asarray(m.indptr, dtype=np.int64)
         self.indices_host = np.asarray(m.indices)
-        self.indptr = torch.from_numpy(self.indptr_host.astype(np.int32)).to(device)
-        self.indices = torch.from_numpy(self.indices_host.astype(np.int32)).to(device)
-        self.data = torch.from_numpy(np.asarray(m.data, dtype=np.float32)).to(device) if with_values else None
+        self.indptr = to_dev(self.indptr_host.astype(np.int32), device)
+        self.indices = to_dev(self.indices_host.astype(np.int32), device)
+        self.data = to_dev(np.asarray(m.data, dtype=np.float32), device) if with_values else None
 
     @property
     def row_len(self):
@@ -93,7 +107,7 @@ class EpochLayout:
 
 def flat_from_state_dict(sd, device):
     """Reference AE state_dict -> the engine's flat layout W1t b1 W2 b2 W3 b3 W4 b4 (include/dmt_b200.h)."""
-    g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    g = lambda k: to_dev(sd[k].detach().to(torch.float32), device)
     return torch.cat([g("encoder_linear.weight").t().contiguous().view(-1), g("encoder_linear.bias"),
                       g("encoder.blocks.0.weight").reshape(-1), g("encoder.blocks.0.bias"),
                       g("decoder.blocks.0.weight").reshape(-1), g("decoder.blocks.0.bias"),
@@ -149,8 +163,10 @@ class OrgEngine:
         self._keep_alive = [params_flat, residual]
 
     def enqueue_epoch(self, layout: EpochLayout, keep=None, seed=0, hp=None, loss_out=None):
-        rows = torch.from_numpy(layout.rows.astype(np.int32)).to(self.device)
-        off = torch.from_numpy(layout.row_off).to(self.device)
+        rows = to_dev(layout.rows.astype(np.int32), self.device)
+        off = to_dev(layout.row_off, self.device)
+        if keep is not None and not keep.is_cuda:
+            keep = to_dev(keep, self.device)
         self.h.wait_current()
         self.h.train_epoch(rows, off, layout.n_t, layout.n_d, keep=keep, seed=seed, epoch_loss=loss_out, **(hp or {}))
         self._keep_alive += [rows, off, keep, loss_out]
@@ -158,8 +174,8 @@ class OrgEngine:
     def enqueue_epochs(self, layouts, seeds, hp=None, loss_out=None):
         """Several epochs with ONE host->device copy of all their row lists (device-generated dropout)."""
         nb = [len(l.row_off) - 1 for l in layouts]
-        rows_all = torch.from_numpy(np.concatenate([l.rows for l in layouts]).astype(np.int32)).to(self.device)
-        off_all = torch.from_numpy(np.concatenate([l.row_off for l in layouts])).to(self.device)
+        rows_all = to_dev(np.concatenate([l.rows for l in layouts]).astype(np.int32), self.device)
+        off_all = to_dev(np.concatenate([l.row_off for l in layouts]), self.device)
         self.h.wait_current()
         r0 = o0 = l0 = 0
         for e, l in enumerate(layouts):
@@ -191,7 +207,7 @@ class OrgEngine:
 class MtalState:
     """Global per-split state of the coordinator (Assist, reference src/assist.py:13-41) on the device."""
 
-    def __init__(self, y: dict, data_split, target_mode, device="cuda"):
+    def __init__(self, y: dict, data_split, target_mode, device="cuda", o_rows=None):
         self.splits = list(y)
         self.y = {k: DeviceCSR(y[k], device) for k in y}
         self.K = len(data_split)
@@ -212,7 +228,9 @@ class MtalState:
         self.owner_host, self.local_host = owner, local
         self.owner = torch.from_numpy(owner).to(device)
         self.data_split = [np.asarray(c, dtype=np.int64) for c in data_split]
-        self.O = {k: torch.zeros(self.K, self.y[k].nnz, device=device) for k in y}
+        # O may carry padding rows so that an in-place all-gather over equal per-rank chunks can fill it (dist.py)
+        self.O_full = {k: torch.zeros(max(self.K, o_rows or 0), self.y[k].nnz, device=device) for k in y}
+        self.O = {k: self.O_full[k][:self.K] for k in y}
         self._views = {}
 
     def residual(self, F, split, clamp, out=None):
@@ -273,8 +291,8 @@ class MtalState:
         opt = torch.optim.LBFGS(free, lr=lr)
 
         def closure():
-            out = native.assist_loss_grad(h, t, V, v["seg_off"], rate.detach().to(self.device),
-                                          weight.detach().to(self.device), self.loss_kind, scratch).cpu()
+            out = to_host(native.assist_loss_grad(h, t, V, v["seg_off"], to_dev(rate.detach(), self.device),
+                                                  to_dev(weight.detach(), self.device), self.loss_kind, scratch))
             if rate.requires_grad:
                 rate.grad = out[1:1 + n_rate].clone()
             if weight.requires_grad:
@@ -293,8 +311,8 @@ class MtalState:
         for i, (rate, weight) in enumerate(fitted):
             rate_col[self.data_split[i]] = rate.numpy()
             S[i] = torch.softmax(weight, -1).numpy()
-        rate_col_d = torch.from_numpy(rate_col).to(self.device)
-        S_d = torch.from_numpy(S).to(self.device)
+        rate_col_d = to_dev(rate_col, self.device)
+        S_d = to_dev(S, self.device)
         F_next = {}
         for k in self.splits:
             me = self.match_end(k, match_rate) if match_rate < 1 else None

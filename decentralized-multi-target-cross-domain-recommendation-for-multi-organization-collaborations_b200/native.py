@@ -83,6 +83,9 @@ def _declare(lib):
         "dmt_org_stream": (P, [P]),
         "dmt_org_wait_stream": (I, [P, P]),
         "dmt_org_signal_stream": (I, [P, P]),
+        "dmt_launch_count": (L, []),
+        "dmt_org_profile_classes": (I, []),
+        "dmt_org_profile_step": (I, [P, I, I, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header and library out of sync: fail loudly
@@ -365,6 +368,16 @@ class Org:
     def signal_current(self):
         """torch's current stream waits for work already enqueued on the organization's stream."""
         check(self._lib.dmt_org_signal_stream(self.h, stream()), "dmt_org_signal_stream")
+
+    PROFILE_CLASSES = ["encoder_spmm", "dense_fwd", "grad_zero", "decoder_loss_dz3", "dw4_segments", "dense_bwd",
+                       "dw1_segments", "grad_norm", "clip_adam"]
+
+    def profile_step(self, b=0, reps=20):
+        """{kernel class: average ms} for one training step on batch b of the current plan (dmt_org_profile_step)."""
+        n = self._lib.dmt_org_profile_classes()
+        buf = (C.c_float * n)()
+        check(self._lib.dmt_org_profile_step(self.h, int(b), int(reps), buf), "dmt_org_profile_step")
+        return dict(zip(self.PROFILE_CLASSES, [float(x) for x in buf]))
 
     def cuda_stream(self):
         return self._lib.dmt_org_stream(self.h)

@@ -1,0 +1,158 @@
+"""Device-resident assistance rounds with organizations sharded over ranks.
+
+One process per GPU. Every rank keeps the global CSR structure, ground truth and current global prediction F_t;
+organization k (its data column block, parameters, optimizer state, epoch plans and CUDA graph) lives on rank
+``k // ceil(K / world)`` (contiguous blocks). Inside a round the ranks share nothing; the only exchange is the K prediction vectors after
+``predict`` (reference: plain Python list passing, src/train_recsys_assist.py:166-172; src/assist.py:81-84):
+an NCCL all-gather of the [K x nnz] organization-major matrix rows over NVLink. After it every
+rank runs the same (cheap, O(K nnz)) ``update`` so F_{t} is replicated without a second collective.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import engine as E
+from . import native
+
+
+def xavier_uniform_(shape, device, generator=None):
+    """nn.init.xavier_uniform_ on the device (production mode: same distribution as the reference's init,
+    src/models/ae.py:22-28,89-96, drawn by the device generator instead of torch's CPU generator)."""
+    fan_out, fan_in = shape
+    a = math.sqrt(6.0 / (fan_in + fan_out))
+    return torch.empty(shape, device=device).uniform_(-a, a, generator=generator)
+
+
+def init_flat_params(n_enc, n_dec, H1, H2, device, generator=None):
+    """Fresh AAE parameters in the engine's flat layout (W1t b1 W2 b2 W3 b3 W4 b4), xavier weights, zero biases."""
+    W1 = xavier_uniform_((H1, n_enc), device, generator)
+    W2 = xavier_uniform_((H2, H1), device, generator)
+    W3 = xavier_uniform_((H1, H2), device, generator)
+    W4 = xavier_uniform_((n_dec, H1), device, generator)
+    z = lambda n: torch.zeros(n, device=device)
+    return torch.cat([W1.t().contiguous().view(-1), z(H1), W2.view(-1), z(H2), W3.view(-1), z(H1), W4.view(-1),
+                      z(n_dec)]).contiguous()
+
+
+class AssistRounds:
+    def __init__(self, mats, data_split, target_mode, batch_rows, clamp=False, ar=0.1, ar_mode="constant",
+                 aw_mode="constant", match_rate=1.0, local_epochs=20, rank=0, world=1, device="cuda", H1=256, H2=128,
+                 seed=0, hp=None):
+        """mats: {'train': (data_csr, target_csr), 'test': (...)} global scipy CSR matrices (rows = aligned entity)."""
+        self.rank, self.world, self.device = rank, world, device
+        self.K = len(data_split)
+        self.target_mode, self.clamp = target_mode, clamp
+        self.ar, self.ar_mode, self.aw_mode, self.match_rate = ar, ar_mode, aw_mode, match_rate
+        self.local_epochs, self.batch_rows, self.seed = local_epochs, batch_rows, seed
+        self.H1, self.H2 = H1, H2
+        self.hp = hp or dict(lr=1e-3, betas=(0.9, 0.999), weight_decay=5e-4, max_norm=1.0)
+        self.splits = list(mats)
+        cols = [np.asarray(c, dtype=np.int64) for c in data_split]
+        y = {k: mats[k][1] for k in mats}
+        for m in y.values():
+            m.sort_indices()
+        self.chunk = -(-self.K // world)  # organizations per rank (contiguous blocks -> in-place all-gather)
+        self.state = E.MtalState(y, cols, target_mode, device, o_rows=self.chunk * world)
+        self.n_rows = y["train"].shape[0]
+        self.my_orgs = list(range(rank * self.chunk, min(self.K, (rank + 1) * self.chunk)))
+        self.org_data, self.org_test_data, self.eng = {}, {}, {}
+        for k in self.my_orgs:
+            d = E.DeviceCSR(mats["train"][0][:, cols[k]].tocsr(), device)
+            self.org_data[k] = d
+            # the test split's data is the train matrix (reference src/datasets/movielens.py:367-371)
+            same = mats["test"][0] is mats["train"][0]
+            self.org_test_data[k] = d if same else E.DeviceCSR(mats["test"][0][:, cols[k]].tocsr(), device)
+            self.eng[k] = E.OrgEngine(d, self.state.y["train"], batch_rows, H1, H2, native.LOSS_KIND[target_mode])
+        self.cols = cols
+        self.mats = mats
+        self.residual = {k: torch.empty(self.state.y[k].nnz, device=device) for k in self.splits}
+        self.F = None
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed * 1000003 + rank)
+        self.host_gen = torch.Generator()
+        self.host_gen.manual_seed(seed * 7919 + rank)
+        self.round_losses = {}
+
+    # ------------------------------------------------------------------ round 0 (replicated: cheap)
+    def round0(self):
+        """models.base per organization -> F_0 (src/organization.py:29-138); every rank computes all organizations."""
+        F = {k: torch.empty(self.state.y[k].nnz, device=self.device) for k in self.splits}
+        implicit = self.target_mode == "implicit"
+        bs = self.batch_rows
+        train_data = self.mats["train"][0]
+        tr = E.DeviceCSR(train_data, self.device)
+        # per-column sums over the whole train data == per-organization base on its own column block
+        base = torch.zeros(tr.shape[1], device=self.device)
+        count = torch.zeros(tr.shape[1], device=self.device)
+        native.base_fit(tr.indices, tr.data, base, count)
+        owner = self.state.owner_host
+        for k in self.splits:
+            yk = self.state.y[k]
+            if not implicit:
+                # unseen columns take the mean of the seen means OF THEIR OWN organization
+                pred = torch.empty(yk.nnz, device=self.device)
+                for i in range(self.K):
+                    ci = torch.from_numpy(self.cols[i]).to(self.device)
+                    pos = torch.from_numpy(self.state.owner_view(k, i)["pos_host"]).to(self.device)
+                    local = torch.from_numpy(self.state.local_host[yk.indices_host[self.state.owner_view(k, i)["pos_host"]]]
+                                             ).to(self.device)
+                    pred[pos] = native.base_predict(base[ci].contiguous(), count[ci].contiguous(), local.contiguous(),
+                                                    False)
+                F[k] = pred
+            else:
+                # count = sum over the organization's loader batches of #rows with data (src/models/base.py:35-37)
+                imp = np.zeros(self.K, np.float32)
+                for i in range(self.K):
+                    rl = np.diff(train_data[:, self.cols[i]].tocsr().indptr)
+                    imp[i] = sum(int((rl[s:s + bs] > 0).sum()) for s in range(0, len(rl), bs))
+                denom = torch.from_numpy(imp[owner]).to(self.device)
+                F[k] = base[yk.indices.long()] / denom[yk.indices.long()]
+        self.F = F
+        return F
+
+    # ------------------------------------------------------------------ one assistance round
+    def run_round(self, t, exchange=None):
+        """make_dataset -> local training of this rank's organizations -> predict -> exchange -> update."""
+        st = self.state
+        for k in self.splits:
+            st.residual(self.F[k], k, self.clamp, out=self.residual[k])
+        loss_bufs = {}
+        for org in self.my_orgs:
+            eng = self.eng[org]
+            flat0 = init_flat_params(eng.n_enc, eng.n_dec, self.H1, self.H2, self.device, self.gen)
+            eng.set_round(flat0, self.residual["train"])
+            layouts = [E.EpochLayout(E.fast_perm_batches(self.n_rows, self.batch_rows, self.host_gen), eng.d_len,
+                                     eng.t_len) for _ in range(self.local_epochs)]
+            seeds = [E.he_seed(self.seed, org, t, e) for e in range(self.local_epochs)]
+            lb = torch.zeros(sum(len(l.active) for l in layouts), device=self.device)
+            eng.enqueue_epochs(layouts, seeds, hp=self.hp, loss_out=lb)
+            loss_bufs[org] = lb
+        for org in self.my_orgs:
+            eng = self.eng[org]
+            eng.predict(self.org_data[org], st.y["train"], st.O["train"][org])
+            eng.predict(self.org_test_data[org], st.y["test"], st.O["test"][org])
+        for org in self.my_orgs:
+            self.eng[org].h.signal_current()  # the current stream waits for every organization's stream
+        if exchange is not None:
+            exchange(st.O)
+        F_next, fitted = st.update(self.F, self.ar, self.ar_mode, self.aw_mode, self.match_rate)
+        self.F = F_next
+        self.round_losses[t] = loss_bufs
+        return F_next, fitted
+
+    def sync(self):
+        for eng in self.eng.values():
+            eng.sync()
+        torch.cuda.synchronize()
+
+    def rating_visits_per_round(self):
+        """Unit of work: K * (epochs * nnz_train + nnz_train + nnz_test)."""
+        n_tr, n_te = self.state.y["train"].nnz, self.state.y["test"].nnz
+        return self.K * (self.local_epochs * n_tr + n_tr + n_te)
+
+    def close(self):
+        for eng in self.eng.values():
+            eng.close()

@@ -199,6 +199,20 @@ void* dmt_org_stream(dmt_org_t* org);
 int dmt_org_wait_stream(dmt_org_t* org, void* stream);
 int dmt_org_signal_stream(dmt_org_t* org, void* stream);
 
+/* ------------------------------------------------------------------ measurement support (bench.py) */
+
+/* Number of kernels of THIS library launched so far in the process (kernels captured in a CUDA graph are counted
+ * once per graph launch). */
+int64_t dmt_launch_count(void);
+/* Average duration in ms of each kernel class of one training step on batch b of the handle's current epoch plan
+ * (call after dmt_org_train_epoch): every class is launched `reps` times back to back between two CUDA events on
+ * the handle's stream; parameters and optimizer state are restored afterwards. ms_out (host) has
+ * dmt_org_profile_classes() entries: 0 encoder SpMM, 1 dense forward (2 GEMMs), 2 gradient zeroing,
+ * 3 decoder+loss+dZ3, 4 dW4 segmented reduction, 5 dense backward (4 GEMMs + 2 column sums),
+ * 6 dW1 segmented reduction + column sum, 7 gradient norm, 8 clip+Adam. */
+int dmt_org_profile_classes(void);
+int dmt_org_profile_step(dmt_org_t* org, int b, int reps, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,12 @@ Layout (only what the path needs):
 """
 __version__ = "0.1.0"
 
+import os as _os0
+
+# Organizations run on private streams (one captured graph each). The default of 8 hardware work queues would alias
+# 18 streams onto 8 queues and serialise them; must be set before the CUDA context exists.
+_os0.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import os as _os
 import sys as _sys
 

@@ -197,6 +197,180 @@ int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int3
     return 0;
 }
 
+// ---------------------------------------------------------------- load-balanced training variant (engine)
+// One block per CHUNK of <= kDecChunk targets of one batch row, so a heavy row (a user with ~2000 ratings) is spread
+// over ~16 blocks instead of serialising one. Each block leaves a partial dZ3 row; the finish kernel adds a row's
+// partials in chunk order (deterministic) and applies the tanh derivative.
+template <int VEC>
+__global__ void __launch_bounds__(256) ae_decoder_chunk_kernel(const int32_t* __restrict__ rows,
+                                                              const int32_t* __restrict__ indptr,
+                                                              const int32_t* __restrict__ indices,
+                                                              const float* __restrict__ target,
+                                                              const float* __restrict__ A3,
+                                                              const float* __restrict__ W4,
+                                                              const float* __restrict__ b4, int loss_kind,
+                                                              const int32_t* __restrict__ n_targets,
+                                                              const int32_t* __restrict__ ent_off, DecChunks dc,
+                                                              float* __restrict__ gout, BatchRef br) {
+    constexpr int H = VEC * 128;
+    constexpr int PER_WARP = kDecChunk / 8;  // 16 targets per warp
+    __shared__ float s_acc[8][H];
+    __shared__ float s_loss[8];
+    int lo, hi;
+    if (!batch_range(br, lo, hi)) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c_lo = dc.batch_chunk_off[br.b], c_hi = dc.batch_chunk_off[br.b + 1];
+    const float inv_n = 1.f / (float)n_targets[br.b];
+    for (int c = c_lo + blockIdx.x; c < c_hi; c += gridDim.x) {
+        const int j = dc.chunk_row[c];  // epoch-wide batch-row index
+        const int u = rows[j];
+        const int k = c - dc.chunk_off[j];
+        const int r0 = indptr[u];
+        const int e0 = r0 + k * kDecChunk;
+        const int e1 = min(indptr[u + 1], e0 + kDecChunk);
+        const int64_t out_base = (int64_t)ent_off[j] - r0;
+        const float* a_row = A3 + (int64_t)(j - lo) * H;
+        float4 a[VEC], acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            a[v] = ld4(a_row + v * 128 + lane * 4);
+            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float loss_acc = 0.f;
+        const int eb = e0 + wid * PER_WARP;
+        const int cnt = max(0, min(PER_WARP, e1 - eb));
+        int c_l = 0;
+        float y_l = 0.f;
+        if (lane < cnt) {
+            c_l = indices[eb + lane];
+            y_l = target[eb + lane];
+        }
+        float o_l = 0.f;
+        int i = 0;
+        for (; i + 4 <= cnt; i += 4) {  // four 1 KB weight rows in flight per warp
+            int cc[4];
+            float4 w[4][VEC];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cc[q] = __shfl_sync(0xffffffffu, c_l, i + q);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) w[q][v] = ld4(W4 + (int64_t)cc[q] * H + v * 128 + lane * 4);
+            float d[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                d[q] = 0.f;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    d[q] += a[v].x * w[q][v].x + a[v].y * w[q][v].y + a[v].z * w[q][v].z + a[v].w * w[q][v].w;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                d[q] = warp_sum(d[q]) + b4[cc[q]];
+                if (lane == i + q) o_l = d[q];
+                const float g = loss_grad(loss_kind, d[q], __shfl_sync(0xffffffffu, y_l, i + q)) * inv_n;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    acc[v].x = fmaf(g, w[q][v].x, acc[v].x);
+                    acc[v].y = fmaf(g, w[q][v].y, acc[v].y);
+                    acc[v].z = fmaf(g, w[q][v].z, acc[v].z);
+                    acc[v].w = fmaf(g, w[q][v].w, acc[v].w);
+                }
+            }
+        }
+        for (; i < cnt; ++i) {
+            const int c0 = __shfl_sync(0xffffffffu, c_l, i);
+            float4 w0[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) w0[v] = ld4(W4 + (int64_t)c0 * H + v * 128 + lane * 4);
+            float d0 = 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) d0 += a[v].x * w0[v].x + a[v].y * w0[v].y + a[v].z * w0[v].z + a[v].w * w0[v].w;
+            d0 = warp_sum(d0) + b4[c0];
+            if (lane == i) o_l = d0;
+            const float g = loss_grad(loss_kind, d0, __shfl_sync(0xffffffffu, y_l, i)) * inv_n;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                acc[v].x = fmaf(g, w0[v].x, acc[v].x);
+                acc[v].y = fmaf(g, w0[v].y, acc[v].y);
+                acc[v].z = fmaf(g, w0[v].z, acc[v].z);
+                acc[v].w = fmaf(g, w0[v].w, acc[v].w);
+            }
+        }
+        if (lane < cnt) {
+            gout[out_base + eb + lane] = loss_grad(loss_kind, o_l, y_l) * inv_n;
+            loss_acc = loss_value(loss_kind, o_l, y_l);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) st4(&s_acc[wid][v * 128 + lane * 4], acc[v]);
+        loss_acc = warp_sum(loss_acc);
+        if (lane == 0) s_loss[wid] = loss_acc;
+        __syncthreads();
+        const int64_t slot = c - c_lo;
+        for (int h = threadIdx.x; h < H; h += 256) {
+            float s = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) s += s_acc[w8][h];
+            dc.dz_part[slot * H + h] = s;
+        }
+        if (threadIdx.x == 0) {
+            float l = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) l += s_loss[w8];
+            dc.loss_part[slot] = l;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) ae_decoder_finish_kernel(const float* __restrict__ A3, int H, DecChunks dc,
+                                                                float* __restrict__ dZ3, float* __restrict__ loss_rows,
+                                                                BatchRef br) {
+    int lo, hi;
+    if (!batch_range(br, lo, hi)) return;
+    const int jl = blockIdx.x;
+    if (jl >= hi - lo) return;
+    const int c_base = dc.batch_chunk_off[br.b];
+    const int c0 = dc.chunk_off[lo + jl] - c_base, c1 = dc.chunk_off[lo + jl + 1] - c_base;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float s = 0.f;
+        for (int c = c0; c < c1; ++c) s += dc.dz_part[(int64_t)c * H + h];
+        const float av = A3[(int64_t)jl * H + h];
+        dZ3[(int64_t)jl * H + h] = s * (1.f - av * av);
+    }
+    if (threadIdx.x == 0) {
+        float l = 0.f;
+        for (int c = c0; c < c1; ++c) l += dc.loss_part[c];
+        loss_rows[jl] = l;
+    }
+}
+
+int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
+                             const float* A3, const float* W4, const float* b4, int H, int loss_kind,
+                             const int32_t* n_targets, const int32_t* ent_off, DecChunks dc, float* gout, float* dZ3,
+                             float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st) {
+    if (n_rows_max <= 0) return 0;
+    // persistent over the batch's chunks (count known only on the device); 2 blocks per SM leaves room for the other
+    // organizations' graphs that run concurrently on their own streams
+    const int blocks = kNumSMs * 2;
+#define DMT_DECC(V)                                                                                             \
+    ae_decoder_chunk_kernel<V><<<blocks, 256, 0, st>>>(rows, indptr, indices, target, A3, W4, b4, loss_kind,   \
+                                                       n_targets, ent_off, dc, gout, br)
+    if (H == 128) DMT_DECC(1);
+    else if (H == 256) DMT_DECC(2);
+    else if (H == 384) DMT_DECC(3);
+    else if (H == 512) DMT_DECC(4);
+    else {
+        set_error("decoder hidden size must be 128, 256, 384 or 512");
+        return DMT_E_ARG;
+    }
+#undef DMT_DECC
+    DMT_LAUNCH_CHECK();
+    ae_decoder_finish_kernel<<<n_rows_max, 256, 0, st>>>(A3, H, dc, dZ3, loss_rows, br);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace dmt
 
 using namespace dmt;

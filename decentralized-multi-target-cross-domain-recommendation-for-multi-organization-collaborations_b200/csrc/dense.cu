@@ -6,14 +6,18 @@
 
 namespace dmt {
 
-constexpr int BK = 16;
+constexpr int BK = 32;
 
+// C = op(A) op(B) with a fused epilogue. 256 threads, BM x BN tile, (BM/16) x (BN/16) outputs per thread.
+// Global -> register prefetch of k-tile t+1 overlaps the FFMA loop on k-tile t (double-buffered shared memory, one
+// barrier per k-tile): these GEMMs are tiny (M = one 500-row batch), so latency, not bandwidth, is what is hidden.
 template <int BM, int BN, bool A_KMAJOR, bool B_KMAJOR, int DYN /*0: M dynamic, 1: K dynamic*/, class Epi>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, int M,
                                                     int N, int K, int lda, int ldb, Epi epi, BatchRef br) {
     constexpr int TM = BM / 16, TN = BN / 16;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
+    constexpr int LA = BM * BK / 256, LB = BN * BK / 256;
+    __shared__ float As[2][BK][BM + 4];
+    __shared__ float Bs[2][BK][BN + 4];
     int lo, hi;
     if (!batch_range(br, lo, hi)) return;
     if (DYN == 0) M = hi - lo; else K = hi - lo;
@@ -25,38 +29,67 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    float ra[LA], rb[LB];
+    auto gload = [&](int k0) {
 #pragma unroll
-        for (int idx = tid; idx < BM * BK; idx += 256) {
+        for (int i = 0; i < LA; ++i) {
+            const int idx = tid + i * 256;
             int m, k;
             if (A_KMAJOR) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
-            int gm = m0 + m, gk = k0 + k;
+            const int gm = m0 + m, gk = k0 + k;
             float v = 0.f;
             if (gm < M && gk < K) v = A_KMAJOR ? A[(int64_t)gm * lda + gk] : A[(int64_t)gk * lda + gm];
-            As[k][m] = v;
+            ra[i] = v;
         }
 #pragma unroll
-        for (int idx = tid; idx < BN * BK; idx += 256) {
+        for (int i = 0; i < LB; ++i) {
+            const int idx = tid + i * 256;
             int n, k;
             if (B_KMAJOR) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
-            int gn = n0 + n, gk = k0 + k;
+            const int gn = n0 + n, gk = k0 + k;
             float v = 0.f;
             if (gn < N && gk < K) v = B_KMAJOR ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn];
-            Bs[k][n] = v;
+            rb[i] = v;
         }
-        __syncthreads();
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int idx = tid + i * 256;
+            int m, k;
+            if (A_KMAJOR) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
+            As[buf][k][m] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int idx = tid + i * 256;
+            int n, k;
+            if (B_KMAJOR) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
+            Bs[buf][k][n] = rb[i];
+        }
+    };
+    const int nk = (K + BK - 1) / BK;
+    if (nk > 0) {
+        gload(0);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int t = 0; t < nk; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < nk) gload((t + 1) * BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+            for (int i = 0; i < TM; ++i) a[i] = As[buf][kk][ty * TM + i];
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+            for (int j = 0; j < TN; ++j) b[j] = Bs[buf][kk][tx * TN + j];
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+        if (t + 1 < nk) sstore(buf ^ 1);
         __syncthreads();
     }
 #pragma unroll
@@ -115,10 +148,11 @@ struct StoreEpi {
     __device__ __forceinline__ void operator()(int m, int n, float acc) const { C[(int64_t)m * ld + n] = acc; }
 };
 
-// db[n] = sum over the batch rows of dY[:, n]
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dY, int n, float* __restrict__ db,
-                                                     BatchRef br) {
-    __shared__ float sh[8][33];
+// db[n] = sum over the batch rows of dY[:, n]. 32 columns x 32 row-lanes per block: the row loop is 32x shorter than
+// the batch (latency, not bandwidth, is what this tiny reduction costs).
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ dY, int n, float* __restrict__ db,
+                                                      BatchRef br) {
+    __shared__ float sh[32][33];
     int lo, hi;
     if (!batch_range(br, lo, hi)) return;
     int m = hi - lo;
@@ -126,13 +160,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     int col = blockIdx.x * 32 + x;
     float s = 0.f;
     if (col < n)
-        for (int r = y; r < m; r += 8) s += dY[(int64_t)r * n + col];
+        for (int r = y; r < m; r += 32) s += dY[(int64_t)r * n + col];
     sh[y][x] = s;
     __syncthreads();
     if (y == 0 && col < n) {
         float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += sh[i][x];
+        for (int i = 0; i < 32; ++i) t += sh[i][x];
         db[col] = t;
     }
 }
@@ -175,7 +209,7 @@ int launch_dense_bwd_w(const float* dY, const float* X, float* dW, float* db, in
 }
 
 int launch_colsum(const float* dY, int n, float* db, BatchRef br, cudaStream_t st) {
-    colsum_kernel<<<(n + 31) / 32, 256, 0, st>>>(dY, n, db, br);
+    colsum_kernel<<<(n + 31) / 32, 1024, 0, st>>>(dY, n, db, br);
     DMT_LAUNCH_CHECK();
     return 0;
 }

@@ -4,7 +4,7 @@
 // Per local epoch (one call):
 //   plan   : from the epoch's row order build, for targets and data, the batch-ordered entry space, its stable
 //            sort by (batch, column) and the (batch, column) segments  -> no per-batch host work at all
-//   steps  : for every batch one fixed sequence of 17 kernels + 1 memset (forward, fused decoder/loss/first
+//   steps  : for every batch one fixed sequence of 20 kernels (forward, fused decoder/loss/first
 //            backward product, segmented gradient reductions, dense backward, global-norm clip + Adam); every
 //            kernel reads its batch bounds from device memory, so the whole epoch is ONE CUDA graph that is
 //            captured once and replayed for every epoch of every round.
@@ -30,6 +30,14 @@ struct PlanSide {  // per-matrix (targets or data) epoch plan buffers
     int32_t* n_seg = nullptr;       // [1]
     int32_t* batch_seg_off = nullptr;  // [nb_cap + 1]
     int32_t* batch_cnt = nullptr;   // [nb_cap] entries per batch
+    // load-balanced segmented reduction: segments cut into chunks of <= kSegChunk entries
+    int32_t* n_ch = nullptr;           // [cap + 2]
+    int32_t* seg_chunk_off = nullptr;  // [cap + 2]
+    int32_t* chunk_seg = nullptr;      // [chunk_cap]
+    int32_t* batch_chunk_off = nullptr;  // [nb_cap + 2]
+    float* part = nullptr;             // [part_rows x H1]
+    float* part_bias = nullptr;        // [part_rows]
+    int64_t chunk_cap = 0, part_rows = 0;
 };
 
 }  // namespace dmt
@@ -58,6 +66,10 @@ struct dmt_org {
     float* dval_ord;  // [d cap] data values in batch-ordered entry space
     int32_t* row_batch;  // [rows_cap]
     int32_t* active;     // [nb_cap]
+    // decoder row chunks (<= kDecChunk targets each)
+    int32_t *t_nch_row, *t_chunk_off, *t_chunk_row, *t_batch_chunk;
+    float *dz_part, *loss_part;
+    int64_t dec_chunk_cap, dec_part_rows;
     void* sort_temp;
     int64_t sort_temp_bytes;
     // epoch inputs (stable addresses for the graph)
@@ -74,7 +86,8 @@ struct dmt_org {
     // graph cache
     cudaGraphExec_t exec;
     long long g_kernels;  // our kernel launches captured in the graph
-    int g_nb, g_keep;
+    int g_nb, g_keep, g_rows;
+    int64_t g_nt, g_nd;
     AdamHyper g_hp;
 };
 
@@ -89,9 +102,17 @@ static int dalloc(T** p, int64_t n) {
     return 0;
 }
 
-static int alloc_side(PlanSide& s, int64_t cap, int rows_cap, int nb_cap) {
+static int alloc_side(PlanSide& s, int64_t cap, int rows_cap, int nb_cap, int n_cols, int H) {
     s.cap = cap;
+    s.chunk_cap = cap + cap / kSegChunk + 16;
+    s.part_rows = (int64_t)n_cols + cap / kSegChunk + 16;
     int rc = 0;
+    if ((rc = dalloc(&s.n_ch, cap + 2))) return rc;
+    if ((rc = dalloc(&s.seg_chunk_off, cap + 2))) return rc;
+    if ((rc = dalloc(&s.chunk_seg, s.chunk_cap))) return rc;
+    if ((rc = dalloc(&s.batch_chunk_off, nb_cap + 2))) return rc;
+    if ((rc = dalloc(&s.part, s.part_rows * H))) return rc;
+    if ((rc = dalloc(&s.part_bias, s.part_rows))) return rc;
     if ((rc = dalloc(&s.ent_off, rows_cap + 2))) return rc;
     if ((rc = dalloc(&s.len, rows_cap + 2))) return rc;
     if ((rc = dalloc(&s.key, cap))) return rc;
@@ -108,6 +129,8 @@ static int alloc_side(PlanSide& s, int64_t cap, int rows_cap, int nb_cap) {
 static void free_side(PlanSide& s) {
     cudaFree(s.ent_off); cudaFree(s.len); cudaFree(s.key); cudaFree(s.ent_row); cudaFree(s.perm);
     cudaFree(s.seg_key); cudaFree(s.seg_off); cudaFree(s.n_seg); cudaFree(s.batch_seg_off); cudaFree(s.batch_cnt);
+    cudaFree(s.n_ch); cudaFree(s.seg_chunk_off); cudaFree(s.chunk_seg); cudaFree(s.batch_chunk_off);
+    cudaFree(s.part); cudaFree(s.part_bias);
 }
 
 // ---------------------------------------------------------------- plan kernels
@@ -183,6 +206,26 @@ __global__ void plan_batch_seg_kernel(const int32_t* __restrict__ seg_key, const
     batch_seg_off[b] = lo;
 }
 
+__global__ void plan_row_chunks_kernel(const int32_t* __restrict__ tlen, int n, int32_t* __restrict__ nch) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n) return;
+    nch[j] = j < n ? (tlen[j] + kDecChunk - 1) / kDecChunk : 0;
+}
+
+__global__ void plan_row_chunk_fill_kernel(const int32_t* __restrict__ chunk_off, int n,
+                                           int32_t* __restrict__ chunk_row) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int c = chunk_off[j]; c < chunk_off[j + 1]; ++c) chunk_row[c] = j;
+}
+
+// out[b] = src[idx[b]] for b in [0, nb]
+__global__ void plan_gather_offsets_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int nb,
+                                           int32_t* __restrict__ out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= nb) out[b] = src[idx[b]];
+}
+
 static int bits_for(int64_t bound) {
     int bits = 1;
     while (bits < 32 && (1LL << bits) < bound) ++bits;
@@ -211,6 +254,20 @@ static int build_plan(dmt_org* o, int n, int nb, int64_t n_t, int64_t n_d) {
     plan_batch_meta_kernel<<<(nb + 127) / 128, 128, 0, st>>>(o->row_off_buf, nb, o->pt.ent_off, o->pd.ent_off,
                                                             o->pt.batch_cnt, o->pd.batch_cnt, o->active);
     DMT_LAUNCH_CHECK();
+    {   // decoder row chunks
+        plan_row_chunks_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(o->pt.len, n, o->t_nch_row);
+        DMT_LAUNCH_CHECK();
+        size_t bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, o->t_nch_row, o->t_chunk_off, n + 1);
+        DMT_CUDA(cub::DeviceScan::ExclusiveSum(o->sort_temp, bytes, o->t_nch_row, o->t_chunk_off, n + 1, st));
+        if (n > 0) {
+            plan_row_chunk_fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(o->t_chunk_off, n, o->t_chunk_row);
+            DMT_LAUNCH_CHECK();
+        }
+        plan_gather_offsets_kernel<<<(nb + 1 + 127) / 128, 128, 0, st>>>(o->t_chunk_off, o->row_off_buf, nb,
+                                                                        o->t_batch_chunk);
+        DMT_LAUNCH_CHECK();
+    }
     int blocks = (n + 7) / 8;
     if (blocks > 0) {
         plan_fill_kernel<<<blocks, 256, 0, st>>>(o->rows_buf, o->row_off_buf, o->row_batch, n, o->t_indptr,
@@ -234,6 +291,17 @@ static int build_plan(dmt_org* o, int n, int nb, int64_t n_t, int64_t n_d) {
     plan_batch_seg_kernel<<<(nb + 1 + 127) / 128, 128, 0, st>>>(o->pd.seg_key, o->pd.n_seg, nb, o->n_enc,
                                                                o->pd.batch_seg_off);
     DMT_LAUNCH_CHECK();
+    PlanSide* sides[2] = {&o->pt, &o->pd};
+    int64_t counts[2] = {n_t, n_d};
+    for (int i = 0; i < 2; ++i) {
+        PlanSide& s = *sides[i];
+        if ((rc = build_seg_chunks(s.seg_off, s.n_seg, counts[i], s.n_ch, s.seg_chunk_off, s.chunk_seg, o->sort_temp,
+                                   o->sort_temp_bytes, st)))
+            return rc;
+        plan_gather_offsets_kernel<<<(nb + 1 + 127) / 128, 128, 0, st>>>(s.seg_chunk_off, s.batch_seg_off, nb,
+                                                                        s.batch_chunk_off);
+        DMT_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -269,18 +337,22 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
         if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, o->a2, drop, B, H2, H1, 1, br, st))) return rc;
         if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, B, H1, H2, 1, br, st))) return rc;
     }
-    if (WANT(K_ZERO)) DMT_CUDA(cudaMemsetAsync(G, 0, (size_t)o->n_params * sizeof(float), st));
+    // (no gradient zeroing pass: Adam clears every gradient it consumes, dmt_org_set_params clears the first)
     // decoder + loss + dZ3
-    if (WANT(K_DEC))
-        if ((rc = launch_ae_decoder_fwd(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1,
-                                        DMT_LOSS_MSE, o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, o->dz3,
-                                        o->loss_rows, 1, B, br, st)))
+    if (WANT(K_DEC)) {
+        DecChunks dc{o->t_chunk_off, o->t_chunk_row, o->t_batch_chunk, o->dz_part, o->loss_part};
+        if ((rc = launch_ae_decoder_chunks(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1,
+                                           DMT_LOSS_MSE, o->pt.batch_cnt, o->pt.ent_off, dc, o->gbuf, o->dz3,
+                                           o->loss_rows, B, br, st)))
             return rc;
+    }
     // dW4, db4: segmented over (batch, target column)
     if (WANT(K_SEG_W4)) {
-        SegRef st4{o->pt.batch_seg_off, nullptr, b, 0, 0, o->n_dec};
-        if ((rc = launch_segment_reduce_rows(o->pt.perm, o->pt.seg_key, o->pt.seg_off, st4, o->n_dec, o->gbuf,
-                                             o->pt.ent_row, o->a3, H1, G + o->oW4, G + o->ob4, o->active, st)))
+        ChunkedSegs cs{o->pt.perm, o->pt.ent_row, o->pt.seg_key, o->pt.seg_off, o->pt.batch_seg_off,
+                       o->pt.seg_chunk_off, o->pt.chunk_seg, o->pt.batch_chunk_off, o->pt.part, o->pt.part_bias, b,
+                       o->n_dec};
+        if ((rc = launch_segment_chunks(cs, o->n_dec * 2, o->n_dec, o->gbuf, o->a3, H1, G + o->oW4, G + o->ob4,
+                                        o->active, st)))
             return rc;
     }
     // dense backward
@@ -292,9 +364,11 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
     }
     // dW1t: segmented over (batch, data column); db1 = column sums of dZ1
     if (WANT(K_SEG_W1)) {
-        SegRef sd{o->pd.batch_seg_off, nullptr, b, 0, 0, o->n_enc};
-        if ((rc = launch_segment_reduce_rows(o->pd.perm, o->pd.seg_key, o->pd.seg_off, sd, o->n_enc, o->dval_ord,
-                                             o->pd.ent_row, o->dz1, H1, G + o->oW1, nullptr, o->active, st)))
+        ChunkedSegs cs{o->pd.perm, o->pd.ent_row, o->pd.seg_key, o->pd.seg_off, o->pd.batch_seg_off,
+                       o->pd.seg_chunk_off, o->pd.chunk_seg, o->pd.batch_chunk_off, o->pd.part, o->pd.part_bias, b,
+                       o->n_enc};
+        if ((rc = launch_segment_chunks(cs, o->n_enc * 2, o->n_enc, o->dval_ord, o->dz1, H1, G + o->oW1, nullptr,
+                                        o->active, st)))
             return rc;
         if ((rc = launch_colsum(o->dz1, H1, G + o->ob1, br, st))) return rc;
     }
@@ -305,7 +379,7 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
         if ((rc = launch_adam_prepare(o->partial, kNormBlocks, nullptr, nullptr, o->sc, hp, 0, o->step_dev,
                                       o->loss_rows, o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
             return rc;
-        if ((rc = launch_adam(o->P, G, o->M, o->V, o->n_params, o->sc, hp, st))) return rc;
+        if ((rc = launch_adam(o->P, G, o->M, o->V, o->n_params, o->sc, hp, true, st))) return rc;
     }
 #undef WANT
     return 0;
@@ -323,6 +397,8 @@ static int free_all(dmt_org* o) {
     cudaFree(o->dz1); cudaFree(o->loss_rows); cudaFree(o->iota_rows);
     free_side(o->pt); free_side(o->pd);
     cudaFree(o->gbuf); cudaFree(o->dval_ord); cudaFree(o->row_batch); cudaFree(o->active); cudaFree(o->sort_temp);
+    cudaFree(o->t_nch_row); cudaFree(o->t_chunk_off); cudaFree(o->t_chunk_row); cudaFree(o->t_batch_chunk);
+    cudaFree(o->dz_part); cudaFree(o->loss_part);
     cudaFree(o->rows_buf); cudaFree(o->row_off_buf); cudaFree(o->keep_buf); cudaFree(o->seed_dev);
     cudaFree(o->loss_buf); cudaFree(o->partial); cudaFree(o->sc); cudaFree(o->step_dev);
     if (o->ev) cudaEventDestroy(o->ev);
@@ -385,7 +461,13 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     A(dalloc(&o->dz3, (int64_t)batch_rows * H1)); A(dalloc(&o->dz2, (int64_t)batch_rows * H2));
     A(dalloc(&o->dz1, (int64_t)batch_rows * H1)); A(dalloc(&o->loss_rows, batch_rows));
     A(dalloc(&o->iota_rows, n_rows));
-    A(alloc_side(o->pt, t_nnz, o->rows_cap, o->nb_cap)); A(alloc_side(o->pd, d_nnz, o->rows_cap, o->nb_cap));
+    A(alloc_side(o->pt, t_nnz, o->rows_cap, o->nb_cap, n_dec, H1));
+    A(alloc_side(o->pd, d_nnz, o->rows_cap, o->nb_cap, n_enc, H1));
+    o->dec_chunk_cap = t_nnz / kDecChunk + o->rows_cap + 16;
+    o->dec_part_rows = t_nnz / kDecChunk + batch_rows + 16;
+    A(dalloc(&o->t_nch_row, o->rows_cap + 2)); A(dalloc(&o->t_chunk_off, o->rows_cap + 2));
+    A(dalloc(&o->t_chunk_row, o->dec_chunk_cap)); A(dalloc(&o->t_batch_chunk, o->nb_cap + 2));
+    A(dalloc(&o->dz_part, o->dec_part_rows * H1)); A(dalloc(&o->loss_part, o->dec_part_rows));
     A(dalloc(&o->gbuf, t_nnz)); A(dalloc(&o->dval_ord, d_nnz)); A(dalloc(&o->row_batch, o->rows_cap + 1));
     A(dalloc(&o->active, o->nb_cap + 1));
     o->sort_temp_bytes = sort_segments_temp_bytes(t_nnz > d_nnz ? t_nnz : d_nnz);
@@ -403,6 +485,7 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     cudaMemsetAsync(o->step_dev, 0, sizeof(int), o->st);
     cudaMemsetAsync(o->M, 0, (size_t)o->n_params * 4, o->st);
     cudaMemsetAsync(o->V, 0, (size_t)o->n_params * 4, o->st);
+    cudaMemsetAsync(o->G, 0, (size_t)o->n_params * 4, o->st);
     o->exec = nullptr;
     o->g_nb = -1;
     *out = o;
@@ -424,6 +507,7 @@ int dmt_org_set_params(dmt_org_t* o, const float* flat) {
     DMT_CUDA(cudaMemcpyAsync(o->P, flat, (size_t)o->n_params * 4, cudaMemcpyDeviceToDevice, o->st));
     DMT_CUDA(cudaMemsetAsync(o->M, 0, (size_t)o->n_params * 4, o->st));
     DMT_CUDA(cudaMemsetAsync(o->V, 0, (size_t)o->n_params * 4, o->st));
+    DMT_CUDA(cudaMemsetAsync(o->G, 0, (size_t)o->n_params * 4, o->st));
     DMT_CUDA(cudaMemsetAsync(o->step_dev, 0, sizeof(int), o->st));
     return 0;
 }
@@ -461,15 +545,19 @@ int dmt_org_train_epoch(dmt_org_t* o, const int32_t* rows, const int32_t* row_of
     DMT_CUDA(cudaMemcpyAsync(o->row_off_buf, row_off, (size_t)(n_batches + 1) * 4, cudaMemcpyDeviceToDevice, st));
     if (keep) DMT_CUDA(cudaMemcpyAsync(o->keep_buf, keep, (size_t)n_rows_total * o->H2, cudaMemcpyDeviceToDevice, st));
     DMT_CUDA(cudaMemcpyAsync(o->seed_dev, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
-    int rc = build_plan(o, n_rows_total, n_batches, n_t_entries, n_d_entries);
-    if (rc) return rc;
+    int rc = 0;
     AdamHyper hp{lr, beta1, beta2, eps, weight_decay, max_norm};
     int use_keep = keep != nullptr;
-    if (!o->exec || o->g_nb != n_batches || o->g_keep != use_keep || !same_hp(hp, o->g_hp)) {
+    // The whole epoch — plan (scans, the two radix sorts, segment/chunk tables) AND the per-batch steps — is one graph:
+    // one launch per epoch from the host. Entry totals are baked into the captured sort calls, so the graph is keyed
+    // on them too (they are constant for epochs that cover every row).
+    if (!o->exec || o->g_nb != n_batches || o->g_keep != use_keep || !same_hp(hp, o->g_hp) ||
+        o->g_rows != n_rows_total || o->g_nt != n_t_entries || o->g_nd != n_d_entries) {
         if (o->exec) { cudaGraphExecDestroy(o->exec); o->exec = nullptr; }
         cudaGraph_t graph = nullptr;
         DMT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         long long before = launch_count();
+        rc = build_plan(o, n_rows_total, n_batches, n_t_entries, n_d_entries);
         for (int b = 0; b < n_batches && rc == 0; ++b) rc = enqueue_step(o, b, use_keep != 0, hp);
         o->g_kernels = launch_count() - before;
         count_launch(-o->g_kernels);  // captured, not executed: counted at every cudaGraphLaunch instead
@@ -480,6 +568,7 @@ int dmt_org_train_epoch(dmt_org_t* o, const int32_t* rows, const int32_t* row_of
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { o->exec = nullptr; set_error(cudaGetErrorString(e)); return (int)e; }
         o->g_nb = n_batches; o->g_keep = use_keep; o->g_hp = hp;
+        o->g_rows = n_rows_total; o->g_nt = n_t_entries; o->g_nd = n_d_entries;
     }
     DMT_CUDA(cudaGraphLaunch(o->exec, st));
     count_launch(o->g_kernels);

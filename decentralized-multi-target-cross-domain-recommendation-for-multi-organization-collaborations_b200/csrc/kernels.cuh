@@ -20,7 +20,7 @@ int launch_sqnorm_stage1(const float* g, int64_t n, float* partial, BatchRef br,
 int launch_adam_prepare(const float* partial, int n_partial, const float* sqnorm_in, float* sqnorm_out,
                         AdamScalars* sc, AdamHyper hp, int64_t step_by_value, int* step_dev, const float* loss_rows,
                         const int32_t* n_targets_ptr, float* loss_out, BatchRef br, cudaStream_t st);
-int launch_adam(float* w, const float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
+int launch_adam(float* w, float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp, bool zero_g,
                 cudaStream_t st);
 
 // ---- dense.cu   (act: 0 none, 1 tanh, 2 relu)
@@ -83,6 +83,41 @@ struct SegRef {  // segments [seg_lo, seg_hi) either by value or from device bat
 int launch_segment_reduce_rows(const int32_t* perm, const int32_t* seg_key, const int32_t* seg_off, SegRef sr,
                                int64_t n_seg_max, const float* coef, const int32_t* src_row, const float* src,
                                int width, float* grad, float* bias_grad, const int32_t* active, cudaStream_t st);
+// Load-balanced segmented reduction of the engine: segments cut into chunks of <= kSegChunk entries.
+constexpr int kSegChunk = 64;
+struct ChunkedSegs {
+    const int32_t* perm;
+    const int32_t* ent_row;        // in-batch row of every entry (indexes src)
+    const int32_t* seg_key;
+    const int32_t* seg_off;
+    const int32_t* batch_seg_off;  // [nb+1]
+    const int32_t* seg_chunk_off;  // [n_seg+1] first chunk of every segment
+    const int32_t* chunk_seg;      // [n_chunks] owning segment of every chunk
+    const int32_t* batch_chunk_off;  // [nb+1] = seg_chunk_off[batch_seg_off[b]]
+    float* part;                   // [max chunks per batch x width] partial rows of multi-chunk segments
+    float* part_bias;
+    int b;
+    int n_cols;
+};
+int launch_segment_chunks(ChunkedSegs cs, int n_chunk_max, int n_seg_max, const float* coef, const float* src,
+                          int width, float* grad, float* bias_grad, const int32_t* active, cudaStream_t st);
+int build_seg_chunks(const int32_t* seg_off, const int32_t* n_seg, int64_t cap, int32_t* n_ch, int32_t* seg_chunk_off,
+                     int32_t* chunk_seg, void* temp, int64_t temp_bytes, cudaStream_t st);
+
+// Decoder of the engine: batch rows cut into chunks of <= kDecChunk target entries (heavy rows span several blocks).
+constexpr int kDecChunk = 128;
+struct DecChunks {
+    const int32_t* chunk_off;        // [rows+1] first chunk of every batch-row (epoch-wide numbering)
+    const int32_t* chunk_row;        // [n_chunks] batch-row (epoch-wide index) of every chunk
+    const int32_t* batch_chunk_off;  // [nb+1]
+    float* dz_part;                  // [max chunks per batch x H]
+    float* loss_part;                // [max chunks per batch]
+};
+int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
+                             const float* A3, const float* W4, const float* b4, int H, int loss_kind,
+                             const int32_t* n_targets, const int32_t* ent_off, DecChunks dc, float* gout, float* dZ3,
+                             float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st);
+
 int64_t sort_segments_temp_bytes(int64_t n);
 int sort_segments(const uint32_t* keys, int64_t n, int key_bits, int32_t* perm, int32_t* seg_key, int32_t* seg_off,
                   int32_t* n_seg, void* temp, int64_t temp_bytes, cudaStream_t st);

@@ -69,7 +69,8 @@ __global__ void adam_prepare_kernel(const float* __restrict__ partial, int n_par
     }
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g,
+template <bool ZERO_G>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    const AdamScalars* __restrict__ sc, AdamHyper hp) {
     if (sc->active == 0) return;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const 
         st4(w + 4 * i, w4);
         st4(m + 4 * i, m4);
         st4(v + 4 * i, v4);
+        if (ZERO_G) st4(g + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));  // consumed: clear for the next step
     }
     for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float gg = g[i] * coef + wd * w[i];
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const 
         w[i] = w[i] - step_size * (mm / denom);
         m[i] = mm;
         v[i] = vv;
+        if (ZERO_G) g[i] = 0.f;
     }
     (void)b1;
 }
@@ -123,12 +126,13 @@ int launch_adam_prepare(const float* partial, int n_partial, const float* sqnorm
     return 0;
 }
 
-int launch_adam(float* w, const float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
-                cudaStream_t st) {
+int launch_adam(float* w, float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
+                bool zero_g, cudaStream_t st) {
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;
-    adam_kernel<<<(int)blocks, 256, 0, st>>>(w, g, m, v, n, sc, hp);
+    if (zero_g) adam_kernel<true><<<(int)blocks, 256, 0, st>>>(w, g, m, v, n, sc, hp);
+    else adam_kernel<false><<<(int)blocks, 256, 0, st>>>(w, g, m, v, n, sc, hp);
     DMT_LAUNCH_CHECK();
     return 0;
 }
@@ -162,7 +166,7 @@ int dmt_adam_clip_step(float* w, const float* g, float* m, float* v, int64_t n, 
     int rc = launch_adam_prepare(nullptr, 0, sqnorm, nullptr, sc, hp, step, nullptr, nullptr, nullptr, nullptr,
                                  batch_by_value(0, 1), st);
     if (rc) return rc;
-    return launch_adam(w, g, m, v, n, sc, hp, st);
+    return launch_adam(w, const_cast<float*>(g), m, v, n, sc, hp, false, st);
 }
 
 }  // extern "C"

@@ -163,6 +163,191 @@ int launch_segment_reduce_rows(const int32_t* perm, const int32_t* seg_key, cons
     return 0;
 }
 
+// ---------------------------------------------------------------- load-balanced variant used by the engine
+// A segment (one (batch, column) run of the sorted entries) is cut into chunks of <= kSegChunk entries; one warp
+// reduces one chunk with 4 source rows in flight. Single-chunk segments write their gradient row directly;
+// multi-chunk segments (popular columns: up to one entry per batch row) write partial rows that a second small
+// kernel adds in chunk order -> still deterministic, and the critical path is one chunk, not the longest segment.
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_chunks_kernel(ChunkedSegs cs, const float* __restrict__ coef,
+                                                             const float* __restrict__ src, float* __restrict__ grad,
+                                                             float* __restrict__ bias_grad,
+                                                             const int32_t* __restrict__ active) {
+    constexpr int W = VEC * 128;
+    if (active != nullptr && active[cs.b] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int c_lo = cs.batch_chunk_off[cs.b], c_hi = cs.batch_chunk_off[cs.b + 1];
+    const uint32_t key_base = (uint32_t)cs.b * (uint32_t)cs.n_cols;
+    const int warp = blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = gridDim.x * 8;
+    for (int c = c_lo + warp; c < c_hi; c += n_warps) {
+        const int s = cs.chunk_seg[c];
+        const int k = c - cs.seg_chunk_off[s];
+        const int n_ch = cs.seg_chunk_off[s + 1] - cs.seg_chunk_off[s];
+        const int e0 = cs.seg_off[s] + k * kSegChunk;
+        const int e1 = min(cs.seg_off[s + 1], e0 + kSegChunk);
+        float4 acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bsum = 0.f;
+        for (int eb = e0; eb < e1; eb += 32) {
+            int e = eb + lane;
+            float c_l = 0.f;
+            int r_l = 0;
+            if (e < e1) {
+                int id = cs.perm[e];
+                c_l = coef[id];
+                r_l = cs.ent_row[id];
+            }
+            bsum += c_l;
+            const int cnt = min(32, e1 - eb);
+            int i = 0;
+            for (; i + 4 <= cnt; i += 4) {  // 4 independent 1 KB source rows in flight per warp
+                float cc[4];
+                int rr[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    cc[q] = __shfl_sync(0xffffffffu, c_l, i + q);
+                    rr[q] = __shfl_sync(0xffffffffu, r_l, i + q);
+                }
+                float4 x[4][VEC];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) x[q][v] = ld4(src + (int64_t)rr[q] * W + v * 128 + lane * 4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        acc[v].x = fmaf(cc[q], x[q][v].x, acc[v].x);
+                        acc[v].y = fmaf(cc[q], x[q][v].y, acc[v].y);
+                        acc[v].z = fmaf(cc[q], x[q][v].z, acc[v].z);
+                        acc[v].w = fmaf(cc[q], x[q][v].w, acc[v].w);
+                    }
+            }
+            for (; i < cnt; ++i) {
+                const float c1 = __shfl_sync(0xffffffffu, c_l, i);
+                const int r1 = __shfl_sync(0xffffffffu, r_l, i);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float4 x = ld4(src + (int64_t)r1 * W + v * 128 + lane * 4);
+                    acc[v].x = fmaf(c1, x.x, acc[v].x);
+                    acc[v].y = fmaf(c1, x.y, acc[v].y);
+                    acc[v].z = fmaf(c1, x.z, acc[v].z);
+                    acc[v].w = fmaf(c1, x.w, acc[v].w);
+                }
+            }
+        }
+        bsum = warp_sum(bsum);
+        if (n_ch == 1) {
+            const int row_out = (int)((uint32_t)cs.seg_key[s] - key_base);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) st4(grad + (int64_t)row_out * W + v * 128 + lane * 4, acc[v]);
+            if (bias_grad != nullptr && lane == 0) bias_grad[row_out] = bsum;
+        } else {
+            const int64_t slot = c - c_lo;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) st4(cs.part + slot * W + v * 128 + lane * 4, acc[v]);
+            if (lane == 0) cs.part_bias[slot] = bsum;
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_finish_kernel(ChunkedSegs cs, float* __restrict__ grad,
+                                                             float* __restrict__ bias_grad,
+                                                             const int32_t* __restrict__ active) {
+    constexpr int W = VEC * 128;
+    if (active != nullptr && active[cs.b] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int s_lo = cs.batch_seg_off[cs.b], s_hi = cs.batch_seg_off[cs.b + 1];
+    const int c_base = cs.batch_chunk_off[cs.b];
+    const uint32_t key_base = (uint32_t)cs.b * (uint32_t)cs.n_cols;
+    const int warp = blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = gridDim.x * 8;
+    for (int s = s_lo + warp; s < s_hi; s += n_warps) {
+        const int c0 = cs.seg_chunk_off[s], c1 = cs.seg_chunk_off[s + 1];
+        if (c1 - c0 <= 1) continue;
+        float4 acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bsum = 0.f;
+        for (int c = c0; c < c1; ++c) {
+            const int64_t slot = c - c_base;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float4 x = ld4(cs.part + slot * W + v * 128 + lane * 4);
+                acc[v].x += x.x; acc[v].y += x.y; acc[v].z += x.z; acc[v].w += x.w;
+            }
+            bsum += cs.part_bias[slot];
+        }
+        const int row_out = (int)((uint32_t)cs.seg_key[s] - key_base);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) st4(grad + (int64_t)row_out * W + v * 128 + lane * 4, acc[v]);
+        if (bias_grad != nullptr && lane == 0) bias_grad[row_out] = bsum;
+    }
+}
+
+int launch_segment_chunks(ChunkedSegs cs, int n_chunk_max, int n_seg_max, const float* coef, const float* src,
+                          int width, float* grad, float* bias_grad, const int32_t* active, cudaStream_t st) {
+    int blocks = (n_chunk_max + 7) / 8;
+    if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
+    if (blocks < 1) blocks = 1;
+    int fblocks = (n_seg_max + 7) / 8;
+    if (fblocks > kNumSMs) fblocks = kNumSMs;
+    if (fblocks < 1) fblocks = 1;
+#define DMT_SEGC(V)                                                                                   \
+    do {                                                                                              \
+        segment_chunks_kernel<V><<<blocks, 256, 0, st>>>(cs, coef, src, grad, bias_grad, active);     \
+        DMT_LAUNCH_CHECK();                                                                           \
+        segment_finish_kernel<V><<<fblocks, 256, 0, st>>>(cs, grad, bias_grad, active);               \
+        DMT_LAUNCH_CHECK();                                                                           \
+    } while (0)
+    if (width == 128) DMT_SEGC(1);
+    else if (width == 256) DMT_SEGC(2);
+    else if (width == 384) DMT_SEGC(3);
+    else if (width == 512) DMT_SEGC(4);
+    else {
+        set_error("segment_chunks: width must be 128, 256, 384 or 512");
+        return DMT_E_ARG;
+    }
+#undef DMT_SEGC
+    return 0;
+}
+
+// chunk tables: n_ch[s] = ceil(len_s / kSegChunk) for s < n_seg (0 beyond), then chunk -> segment map
+__global__ void seg_chunk_count_kernel(const int32_t* __restrict__ seg_off, const int32_t* __restrict__ n_seg,
+                                       int64_t cap, int32_t* __restrict__ n_ch) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > cap) return;
+    int ns = n_seg[0];
+    n_ch[s] = (s < ns) ? (seg_off[s + 1] - seg_off[s] + kSegChunk - 1) / kSegChunk : 0;
+}
+
+__global__ void seg_chunk_fill_kernel(const int32_t* __restrict__ seg_chunk_off, const int32_t* __restrict__ n_seg,
+                                      int32_t* __restrict__ chunk_seg) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg[0]) return;
+    for (int c = seg_chunk_off[s]; c < seg_chunk_off[s + 1]; ++c) chunk_seg[c] = s;
+}
+
+int build_seg_chunks(const int32_t* seg_off, const int32_t* n_seg, int64_t cap, int32_t* n_ch, int32_t* seg_chunk_off,
+                     int32_t* chunk_seg, void* temp, int64_t temp_bytes, cudaStream_t st) {
+    if (cap < 0) cap = 0;
+    seg_chunk_count_kernel<<<(int)((cap + 1 + 255) / 256), 256, 0, st>>>(seg_off, n_seg, cap, n_ch);
+    DMT_LAUNCH_CHECK();
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, n_ch, seg_chunk_off, (int)cap + 1);
+    if ((int64_t)bytes > temp_bytes) {
+        set_error("build_seg_chunks: temp too small");
+        return DMT_E_STATE;
+    }
+    DMT_CUDA(cub::DeviceScan::ExclusiveSum(temp, bytes, n_ch, seg_chunk_off, (int)cap + 1, st));
+    if (cap > 0) {
+        seg_chunk_fill_kernel<<<(int)((cap + 255) / 256), 256, 0, st>>>(seg_chunk_off, n_seg, chunk_seg);
+        DMT_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 }  // namespace dmt
 
 using namespace dmt;

@@ -140,6 +140,31 @@ def state_dict_from_flat(flat, n_enc, n_dec, H1=256, H2=128):
     return out
 
 
+class FastEpochLayout:
+    """Production-mode layout (device-drawn dropout): the row order inside a batch is irrelevant, so the batch is the
+    permutation slice itself — no per-batch sort on the host. Rows with neither data nor targets are still dropped
+    and batches without data entries still skipped (src/models/ae.py:101, src/organization.py:153-155)."""
+
+    def __init__(self, perm, batch_size, d_len, t_len):
+        perm = np.asarray(perm, dtype=np.int64)
+        n = len(perm)
+        bid = np.arange(n) // batch_size
+        keep = (d_len[perm] + t_len[perm]) > 0
+        if not keep.all():
+            perm, bid = perm[keep], bid[keep]
+        nb = (n + batch_size - 1) // batch_size
+        counts = np.bincount(bid, minlength=nb)
+        self.rows = perm
+        self.row_off = np.zeros(nb + 1, np.int32)
+        self.row_off[1:] = np.cumsum(counts)
+        d_per = np.bincount(bid, weights=d_len[perm], minlength=nb)
+        self.active = (d_per > 0).tolist()
+        self.batch_rows = counts.tolist()
+        self.d_per_batch = d_per.astype(np.int64).tolist()
+        self.n_t = int(t_len[perm].sum())
+        self.n_d = int(d_len[perm].sum())
+
+
 class OrgEngine:
     """One organization's AAE on the device (Organization.train / predict, reference src/organization.py:140-217)."""
 

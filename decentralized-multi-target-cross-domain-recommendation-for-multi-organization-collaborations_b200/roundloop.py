@@ -120,16 +120,35 @@ class AssistRounds:
         for k in self.splits:
             st.residual(self.F[k], k, self.clamp, out=self.residual[k])
         loss_bufs = {}
+        layouts, rows_dev, off_dev = {}, {}, {}
         for org in self.my_orgs:
             eng = self.eng[org]
             flat0 = init_flat_params(eng.n_enc, eng.n_dec, self.H1, self.H2, self.device, self.gen)
             eng.set_round(flat0, self.residual["train"])
-            layouts = [E.EpochLayout(E.fast_perm_batches(self.n_rows, self.batch_rows, self.host_gen), eng.d_len,
-                                     eng.t_len) for _ in range(self.local_epochs)]
-            seeds = [E.he_seed(self.seed, org, t, e) for e in range(self.local_epochs)]
-            lb = torch.zeros(sum(len(l.active) for l in layouts), device=self.device)
-            eng.enqueue_epochs(layouts, seeds, hp=self.hp, loss_out=lb)
-            loss_bufs[org] = lb
+            lays = [E.FastEpochLayout(torch.randperm(self.n_rows, generator=self.host_gen).numpy(), self.batch_rows,
+                                      eng.d_len, eng.t_len) for _ in range(self.local_epochs)]
+            layouts[org] = lays
+            rows_dev[org] = E.to_dev(np.concatenate([l.rows for l in lays]).astype(np.int32), self.device)
+            off_dev[org] = E.to_dev(np.concatenate([l.row_off for l in lays]), self.device)
+            loss_bufs[org] = torch.zeros(sum(len(l.active) for l in lays), device=self.device)
+            eng.h.wait_current()
+            eng._keep_alive += [rows_dev[org], off_dev[org], loss_bufs[org]]
+        # epoch-major enqueue: every organization's stream gets work early, so the GPU never waits for the host to
+        # reach the last organization
+        r0 = {org: 0 for org in self.my_orgs}
+        o0 = dict(r0)
+        l0 = dict(r0)
+        for e in range(self.local_epochs):
+            for org in self.my_orgs:
+                lay = layouts[org][e]
+                nb = len(lay.row_off) - 1
+                self.eng[org].h.train_epoch(rows_dev[org][r0[org]:r0[org] + len(lay.rows)],
+                                            off_dev[org][o0[org]:o0[org] + nb + 1], lay.n_t, lay.n_d, keep=None,
+                                            seed=E.he_seed(self.seed, org, t, e),
+                                            epoch_loss=loss_bufs[org][l0[org]:l0[org] + nb], **self.hp)
+                r0[org] += len(lay.rows)
+                o0[org] += nb + 1
+                l0[org] += nb
         for org in self.my_orgs:
             eng = self.eng[org]
             eng.predict(self.org_data[org], st.y["train"], st.O["train"][org])

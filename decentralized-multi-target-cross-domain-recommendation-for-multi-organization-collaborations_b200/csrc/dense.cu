@@ -13,7 +13,7 @@ constexpr int BK = 32;
 // barrier per k-tile): these GEMMs are tiny (M = one 500-row batch), so latency, not bandwidth, is what is hidden.
 template <int BM, int BN, bool A_KMAJOR, bool B_KMAJOR, int DYN /*0: M dynamic, 1: K dynamic*/, class Epi>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, int M,
-                                                    int N, int K, int lda, int ldb, Epi epi, BatchRef br) {
+                                                    int N, int K, int lda, int ldb, Epi epi, BatchRef br, int zK) {
     constexpr int TM = BM / 16, TN = BN / 16;
     constexpr int LA = BM * BK / 256, LB = BN * BK / 256;
     __shared__ float As[2][BK][BM + 4];
@@ -68,15 +68,21 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
             Bs[buf][k][n] = rb[i];
         }
     };
-    const int nk = (K + BK - 1) / BK;
+    // split-K (grid.z slices of zK along K, partial results at epi's z offset) for reductions over many rows
+    int k_base = 0;
+    if (zK > 0) {
+        k_base = blockIdx.z * zK;
+        K = min(K, k_base + zK);
+    }
+    const int nk = (K - k_base + BK - 1) / BK;
     if (nk > 0) {
-        gload(0);
+        gload(k_base);
         sstore(0);
     }
     __syncthreads();
     for (int t = 0; t < nk; ++t) {
         const int buf = t & 1;
-        if (t + 1 < nk) gload((t + 1) * BK);
+        if (t + 1 < nk) gload(k_base + (t + 1) * BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];
@@ -145,8 +151,21 @@ struct BwdXEpi {
 struct StoreEpi {
     float* C;
     int ld;
-    __device__ __forceinline__ void operator()(int m, int n, float acc) const { C[(int64_t)m * ld + n] = acc; }
+    int64_t zstride;  // split-K: slice z writes its partial at C + z * zstride
+    __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+        C[(int64_t)blockIdx.z * zstride + (int64_t)m * ld + n] = acc;
+    }
 };
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t count,
+                                                            float* __restrict__ out) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[(int64_t)z * count + i];  // fixed order: deterministic
+        out[i] = s;
+    }
+}
 
 // db[n] = sum over the batch rows of dY[:, n]. 32 columns x 32 row-lanes per block: the row loop is 32x shorter than
 // the batch (latency, not bandwidth, is what this tiny reduction costs).
@@ -173,15 +192,15 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 
 template <bool AK, bool BKM, int DYN, class Epi>
 static int launch_gemm(const float* A, const float* B, int M, int N, int K, int lda, int ldb, Epi epi, BatchRef br,
-                       cudaStream_t st) {
+                       cudaStream_t st, int splits = 1, int zK = 0) {
     if (M <= 0 || N <= 0) return 0;
-    int64_t big = (int64_t)((M + 63) / 64) * ((N + 63) / 64);
+    int64_t big = (int64_t)((M + 63) / 64) * ((N + 63) / 64) * splits;
     if (big >= kNumSMs) {
-        dim3 grid((N + 63) / 64, (M + 63) / 64);
-        sgemm_kernel<64, 64, AK, BKM, DYN, Epi><<<grid, 256, 0, st>>>(A, B, M, N, K, lda, ldb, epi, br);
+        dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+        sgemm_kernel<64, 64, AK, BKM, DYN, Epi><<<grid, 256, 0, st>>>(A, B, M, N, K, lda, ldb, epi, br, zK);
     } else {
-        dim3 grid((N + 31) / 32, (M + 31) / 32);
-        sgemm_kernel<32, 32, AK, BKM, DYN, Epi><<<grid, 256, 0, st>>>(A, B, M, N, K, lda, ldb, epi, br);
+        dim3 grid((N + 31) / 32, (M + 31) / 32, splits);
+        sgemm_kernel<32, 32, AK, BKM, DYN, Epi><<<grid, 256, 0, st>>>(A, B, M, N, K, lda, ldb, epi, br, zK);
     }
     DMT_LAUNCH_CHECK();
     return 0;
@@ -201,9 +220,33 @@ int launch_dense_bwd_x(const float* dY, const float* W, const float* A_prev, Dro
 
 int launch_dense_bwd_w(const float* dY, const float* X, float* dW, float* db, int m_max, int n, int k, BatchRef br,
                        cudaStream_t st) {
-    StoreEpi epi{dW, k};
-    int rc = launch_gemm<false, false, 1>(dY, X, n, k, m_max, n, k, epi, br, st);
-    if (rc) return rc;
+    int rc;
+    if (br.row_off == nullptr && m_max > 4096) {
+        // many rows (NCF: one row per rating): split the reduction over grid.z, then add the partials in order
+        int splits = (m_max + 2047) / 2048;
+        if (splits > 64) splits = 64;
+        int zK = (m_max + splits - 1) / splits;
+        zK = (zK + BK - 1) / BK * BK;
+        splits = (m_max + zK - 1) / zK;
+        float* part = nullptr;
+        int64_t count = (int64_t)n * k;
+        DMT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)splits * count * sizeof(float), st));
+        StoreEpi pepi{part, k, count};
+        rc = launch_gemm<false, false, 1>(dY, X, n, k, m_max, n, k, pepi, br, st, splits, zK);
+        if (rc == 0) {
+            int blocks = (int)((count + 255) / 256);
+            if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+            splitk_reduce_kernel<<<blocks, 256, 0, st>>>(part, splits, count, dW);
+            count_launch(1);
+        }
+        cudaFreeAsync(part, st);
+        if (rc) return rc;
+        DMT_CUDA(cudaGetLastError());
+    } else {
+        StoreEpi epi{dW, k, 0};
+        rc = launch_gemm<false, false, 1>(dY, X, n, k, m_max, n, k, epi, br, st);
+        if (rc) return rc;
+    }
     if (db != nullptr) return launch_colsum(dY, n, db, br, st);
     return 0;
 }

@@ -159,5 +159,88 @@ class MFFn(torch.autograd.Function):
         return None, None, None, dWu, dWi, dbu.view(-1, 1), dbi.view(-1, 1), dbias, dpu, dpi, None
 
 
+class EmbedCatFn(torch.autograd.Function):
+    """[W_u[user] + b_u[user], W_i[item] + b_i[item]] written straight into one [n x 2H] tower-input buffer
+    (reference src/models/mlp.py:96, nmf.py:127); backward = sort-by-index + segmented row sums."""
+
+    @staticmethod
+    def forward(ctx, user, item, Wu, bu, Wi, bi):
+        _need_cuda(user, Wu)
+        H = Wu.shape[1]
+        out = torch.empty(user.numel(), 2 * H, device=Wu.device, dtype=torch.float32)
+        native.embed_fwd(user, Wu.contiguous(), bu.reshape(-1).contiguous(), out, 0)
+        native.embed_fwd(item, Wi.contiguous(), bi.reshape(-1).contiguous(), out, H)
+        ctx.save_for_backward(user, item)
+        ctx.sizes = (Wu.shape[0], Wi.shape[0], H)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        user, item = ctx.saved_tensors
+        nu, ni, H = ctx.sizes
+        dOut = dOut.contiguous()
+        dWu, dbu = native.embed_bwd(dOut, 0, H, native.sort_segments(user, nu), nu)
+        dWi, dbi = native.embed_bwd(dOut, H, H, native.sort_segments(item, ni), ni)
+        return None, None, dWu, dbu.view(-1, 1), dWi, dbi.view(-1, 1)
+
+
+class GMFLossFn(torch.autograd.Function):
+    """NCF head: pred = sum_d a_d * (u~ (i~ [+pu]) [+ i~ pi])_d + add, fused with the loss
+    (reference src/models/nmf.py:126-146 with the affine layer split into its tower part `add` and GMF part `a`)."""
+
+    @staticmethod
+    def forward(ctx, user, item, rating, Wu, Wi, bu, bi, pu, pi, colscale, add, loss_kind):
+        _need_cuda(user, Wu)
+        Wu_, Wi_ = Wu.contiguous(), Wi.contiguous()
+        bu_, bi_ = bu.reshape(-1).contiguous(), bi.reshape(-1).contiguous()
+        pu_ = pu.contiguous() if pu is not None else None
+        pi_ = pi.contiguous() if pi is not None else None
+        cs = colscale.contiguous()
+        train = any(ctx.needs_input_grad)
+        res = native.mf_fwd(user, item, rating, Wu_, Wi_, bu_, bi_, None, loss_kind, pu_, pi_, want_grad=train,
+                            colscale=cs, add=add.contiguous(), want_q=train)
+        pred, dpred, sums = res[0], res[1], res[2]
+        loss = sums[0] / user.numel()
+        ctx.set_materialize_grads(False)
+        if train:
+            ctx.save_for_backward(user, item, Wu_, Wi_, bu_, bi_, pu_, pi_, cs, dpred, res[3])
+        ctx.mark_non_differentiable(pred)
+        return pred, loss
+
+    @staticmethod
+    def backward(ctx, dpred_in, dloss):
+        if dloss is None:
+            return (None,) * 12
+        user, item, Wu, Wi, bu, bi, pu, pi, cs, dpred, q = ctx.saved_tensors
+        n = user.numel()
+        scale = float(dloss) / n
+        seg_u = native.sort_segments(user, Wu.shape[0])
+        seg_i = native.sort_segments(item, Wi.shape[0])
+        dWu, dbu = native.mf_bwd_table(item, Wi, bi, pu, dpred, scale, seg_u, Wu.shape[0], cs)
+        dWi, dbi = native.mf_bwd_table(user, Wu, bu, pi, dpred, scale, seg_i, Wi.shape[0], cs)
+        dpu = native.mf_bwd_side(user, Wu, bu, dpred, scale, cs) if pu is not None else None
+        dpi = native.mf_bwd_side(item, Wi, bi, dpred, scale, cs) if pi is not None else None
+        dcs = native.weighted_colsum(dpred, q, scale)
+        return (None, None, None, dWu, dWi, dbu.view(-1, 1), dbi.view(-1, 1), dpu, dpi, dcs, dpred * scale, None)
+
+
+class LossFn(torch.autograd.Function):
+    """models.loss_fn (mean) with its gradient, one kernel (reference src/models/utils.py:7-14)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, loss_kind):
+        _need_cuda(pred)
+        dpred, sums = native.loss_fwd(pred.contiguous(), target.contiguous(), loss_kind, ctx.needs_input_grad[0])
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(dpred)
+        ctx.n = pred.numel()
+        return sums[0] / ctx.n
+
+    @staticmethod
+    def backward(ctx, dloss):
+        dpred, = ctx.saved_tensors
+        return dpred * (dloss / ctx.n), None, None
+
+
 def dense(X, weight, bias, act=0, keep=None, scale=1.0):
     return DenseFn.apply(X, weight, bias, act, keep, scale)

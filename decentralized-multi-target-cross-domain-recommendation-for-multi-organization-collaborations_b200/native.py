@@ -63,9 +63,14 @@ def _declare(lib):
         "dmt_sqnorm": (I, [P, L, P, P, P]),
         "dmt_adam_clip_step": (I, [P, P, P, P, L, P, F, D, D, D, D, D, L, P, P]),
         "dmt_mf_scratch_floats": (L, []),
-        "dmt_mf_fwd": (I, [P, P, P, L, P, P, P, P, P, P, P, I, I, P, P, P, P, P]),
-        "dmt_mf_bwd_table": (I, [P, P, P, P, I, P, F, P, P, P, P, L, P, P, P]),
-        "dmt_mf_bwd_side": (I, [P, L, P, P, I, P, F, P, P]),
+        "dmt_mf_fwd": (I, [P, P, P, L, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P]),
+        "dmt_mf_bwd_table": (I, [P, P, P, P, I, P, F, P, P, P, P, L, P, P, P, P]),
+        "dmt_mf_bwd_side": (I, [P, L, P, P, I, P, F, P, P, P]),
+        "dmt_embed_fwd": (I, [P, L, P, P, I, P, I, I, P]),
+        "dmt_embed_bwd": (I, [P, I, I, I, P, P, P, P, L, P, P, P]),
+        "dmt_weighted_colsum_scratch_floats": (L, [I]),
+        "dmt_weighted_colsum": (I, [P, F, P, L, I, I, P, P, P]),
+        "dmt_loss_fwd": (I, [P, P, L, I, P, P, P, P]),
         "dmt_dense_fwd": (I, [P, P, P, P, P, P, F, I, I, I, I, P]),
         "dmt_dense_bwd_x": (I, [P, P, P, P, F, P, I, I, I, I, P]),
         "dmt_dense_bwd_w": (I, [P, P, P, P, I, I, I, P]),
@@ -226,21 +231,25 @@ def adam_clip_step(w, g, m, v, step, sqnorm_t=None, max_norm=1.0, lr=1e-3, betas
                                     int(step), ptr(scratch), stream()), "dmt_adam_clip_step")
 
 
-def mf_fwd(user, item, rating, Wu, Wi, bu, bi, bias, loss_kind, pu=None, pi=None, want_grad=True):
+def mf_fwd(user, item, rating, Wu, Wi, bu, bi, bias, loss_kind, pu=None, pi=None, want_grad=True, colscale=None,
+           add=None, want_q=False):
     lib = load()
     n = user.numel()
     dev = Wu.device
     pred = torch.empty(n, device=dev, dtype=torch.float32)
     dpred = torch.empty(n, device=dev, dtype=torch.float32) if want_grad else None
+    q = torch.empty(n, Wu.shape[1], device=dev, dtype=torch.float32) if want_q else None
     sums = torch.empty(2, device=dev, dtype=torch.float32)
     scratch = torch.empty(lib.dmt_mf_scratch_floats(), device=dev, dtype=torch.float32)
     check(lib.dmt_mf_fwd(ptr(user), ptr(item), ptr(rating), n, ptr(Wu), ptr(Wi), ptr(bu), ptr(bi), ptr(bias), ptr(pu),
-                         ptr(pi), Wu.shape[1], loss_kind, ptr(pred), ptr(dpred), ptr(sums), ptr(scratch), stream()),
-          "dmt_mf_fwd")
+                         ptr(pi), ptr(colscale), ptr(add), Wu.shape[1], loss_kind, ptr(pred), ptr(dpred), ptr(q),
+                         ptr(sums), ptr(scratch), stream()), "dmt_mf_fwd")
+    if want_q:
+        return pred, dpred, sums, q
     return pred, dpred, sums
 
 
-def mf_bwd_table(other, W_other, b_other, p_side, dpred, scale, seg, n_rows):
+def mf_bwd_table(other, W_other, b_other, p_side, dpred, scale, seg, n_rows, colscale=None):
     """Dense grads (dW [n_rows x H], db [n_rows]) of the table whose sorted segments are ``seg``."""
     perm, seg_key, seg_off, n_seg = seg
     H = W_other.shape[1]
@@ -248,16 +257,51 @@ def mf_bwd_table(other, W_other, b_other, p_side, dpred, scale, seg, n_rows):
     db = torch.zeros(n_rows, device=W_other.device, dtype=torch.float32)
     check(load().dmt_mf_bwd_table(ptr(other), ptr(W_other), ptr(b_other), ptr(p_side), H, ptr(dpred), float(scale),
                                   ptr(perm), ptr(seg_key), ptr(seg_off), ptr(n_seg), min(n_rows, other.numel()),
-                                  ptr(dW), ptr(db), stream()), "dmt_mf_bwd_table")
+                                  ptr(colscale), ptr(dW), ptr(db), stream()), "dmt_mf_bwd_table")
     return dW, db
 
 
-def mf_bwd_side(idx, W, b, dpred, scale):
+def mf_bwd_side(idx, W, b, dpred, scale, colscale=None):
     H = W.shape[1]
     d_p = torch.empty(idx.numel(), H, device=W.device, dtype=torch.float32)
-    check(load().dmt_mf_bwd_side(ptr(idx), idx.numel(), ptr(W), ptr(b), H, ptr(dpred), float(scale), ptr(d_p),
-                                 stream()), "dmt_mf_bwd_side")
+    check(load().dmt_mf_bwd_side(ptr(idx), idx.numel(), ptr(W), ptr(b), H, ptr(dpred), float(scale), ptr(colscale),
+                                 ptr(d_p), stream()), "dmt_mf_bwd_side")
     return d_p
+
+
+def embed_fwd(idx, W, b, out, col_off):
+    check(load().dmt_embed_fwd(ptr(idx), idx.numel(), ptr(W), ptr(b), W.shape[1], ptr(out), out.shape[1], col_off,
+                               stream()), "dmt_embed_fwd")
+
+
+def embed_bwd(dOut, col_off, H, seg, n_rows):
+    perm, seg_key, seg_off, n_seg = seg
+    dW = torch.zeros(n_rows, H, device=dOut.device, dtype=torch.float32)
+    db = torch.zeros(n_rows, device=dOut.device, dtype=torch.float32)
+    check(load().dmt_embed_bwd(ptr(dOut), dOut.shape[1], col_off, H, ptr(perm), ptr(seg_key), ptr(seg_off), ptr(n_seg),
+                               min(n_rows, dOut.shape[0]), ptr(dW), ptr(db), stream()), "dmt_embed_bwd")
+    return dW, db
+
+
+def weighted_colsum(g, Q, scale=1.0):
+    lib = load()
+    n, width = Q.shape
+    out = torch.empty(width, device=Q.device, dtype=torch.float32)
+    scratch = torch.empty(lib.dmt_weighted_colsum_scratch_floats(width), device=Q.device, dtype=torch.float32)
+    check(lib.dmt_weighted_colsum(ptr(g), float(scale), ptr(Q), n, width, Q.shape[1], ptr(out), ptr(scratch),
+                                  stream()), "dmt_weighted_colsum")
+    return out
+
+
+def loss_fwd(pred, y, loss_kind, want_grad=True):
+    lib = load()
+    n = pred.numel()
+    dpred = torch.empty_like(pred) if want_grad else None
+    sums = torch.empty(2, device=pred.device, dtype=torch.float32)
+    scratch = torch.empty(lib.dmt_mf_scratch_floats(), device=pred.device, dtype=torch.float32)
+    check(lib.dmt_loss_fwd(ptr(pred), ptr(y), n, loss_kind, ptr(dpred), ptr(sums), ptr(scratch), stream()),
+          "dmt_loss_fwd")
+    return dpred, sums
 
 
 def dense_fwd(X, W, b, act, keep=None, keep_scale=1.0):

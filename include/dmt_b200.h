@@ -108,26 +108,48 @@ int dmt_adam_clip_step(float* w, const float* g, float* m, float* v, int64_t n, 
 
 /* ------------------------------------------------------------------ MF / GMF (src/models/mf.py, GMF branch of nmf.py) */
 
-/* MF forward + loss + per-rating dloss/dpred in one pass (src/models/mf.py:36-48,79-92):
- *   pred = sum_d (Wu[u,d]+bu[u]) (Wi[i,d]+bi[i])  [+ u~.pu[e]] [+ i~.pi[e]]  + bias
- * pu/pi: optional per-rating side-information projections [n x H] (outputs of the user_profile / item_attr Linear)
- * or NULL. H in {128,256,384,512}. dpred may be NULL (eval). sums[0] = sum of per-rating losses (mean = /n),
- * sums[1] = sum of dloss/dpred. scratch >= dmt_mf_scratch_floats() floats. */
+/* MF / GMF forward + loss + per-rating dloss/dpred in one pass (src/models/mf.py:36-48,79-92; nmf.py:122-146):
+ *   q_d  = (Wu[u,d]+bu[u]) * (Wi[i,d]+bi[i] [+ pu[e,d]])  [+ (Wi[i,d]+bi[i]) * pi[e,d]]
+ *   pred = sum_d colscale[d] * q_d + bias [+ add[e]]        (colscale NULL = all ones, bias NULL = 0)
+ * pu/pi: optional per-rating side-information projections [n x H] (outputs of the user_profile / item_attr Linear).
+ * NCF: colscale = the GMF part of the affine weight, add[e] = the MLP-tower part of the logit, q_out [n x H] (may be
+ * NULL) receives q for the affine-weight gradient. H in {128,256,384,512}. dpred may be NULL (eval).
+ * sums[0] = sum of per-rating losses (mean = /n), sums[1] = sum of dloss/dpred. scratch >= dmt_mf_scratch_floats(). */
 int64_t dmt_mf_scratch_floats(void);
 int dmt_mf_fwd(const int32_t* user, const int32_t* item, const float* rating, int64_t n, const float* Wu,
                const float* Wi, const float* bu, const float* bi, const float* bias, const float* pu, const float* pi,
-               int H, int loss_kind, float* pred, float* dpred, float* sums, float* scratch, void* stream);
+               const float* colscale, const float* add, int H, int loss_kind, float* pred, float* dpred, float* q_out,
+               float* sums, float* scratch, void* stream);
 /* Dense gradient of one embedding table and its bias table from the ratings sorted by that table's index
  * (perm/seg_* from dmt_sort_segments on user[] or item[]):
- *   dW[r] = sum_{e: key(e)=r} g_e * (W_other[other[e]] + b_other[other[e]] [+ p_side[e]]),  db[r] = row-sum of dW[r],
- * g_e = dpred[e]*grad_scale. Rows without ratings are not touched (zero dW/db first). */
+ *   dW[r] = colscale * sum_{e: key(e)=r} g_e * (W_other[other[e]] + b_other[other[e]] [+ p_side[e]]),
+ *   db[r] = row-sum of dW[r],  g_e = dpred[e]*grad_scale. Rows without ratings are not touched (zero dW/db first). */
 int dmt_mf_bwd_table(const int32_t* other, const float* W_other, const float* b_other, const float* p_side, int H,
                      const float* dpred, float grad_scale, const int32_t* perm, const int32_t* seg_key,
-                     const int32_t* seg_off, const int32_t* n_seg, int64_t n_seg_max, float* dW, float* db,
-                     void* stream);
-/* d_p[e][:] = g_e * (W[idx[e]] + b[idx[e]]): gradient w.r.t. a side-information projection (src/models/mf.py:82-90). */
+                     const int32_t* seg_off, const int32_t* n_seg, int64_t n_seg_max, const float* colscale, float* dW,
+                     float* db, void* stream);
+/* d_p[e][:] = colscale * g_e * (W[idx[e]] + b[idx[e]]): gradient w.r.t. a side-information projection. */
 int dmt_mf_bwd_side(const int32_t* idx, int64_t n, const float* W, const float* b, int H, const float* dpred,
-                    float grad_scale, float* d_p, void* stream);
+                    float grad_scale, const float* colscale, float* d_p, void* stream);
+
+/* ------------------------------------------------------------------ MLP / NCF tower pieces (src/models/mlp.py, nmf.py) */
+
+/* out[e][col_off + d] = W[idx[e]][d] + b[idx[e]]: embedding with its bias broadcast-added, written into one slice of
+ * the concatenated tower input (row stride ld floats; ld and col_off multiples of 4). */
+int dmt_embed_fwd(const int32_t* idx, int64_t n, const float* W, const float* b, int H, float* out, int ld,
+                  int col_off, void* stream);
+/* Dense gradient of that embedding: dW[r] = sum_{e in segment r} dOut[perm[e]][col_off : col_off+H], db[r] = row-sum. */
+int dmt_embed_bwd(const float* dOut, int ld, int col_off, int H, const int32_t* perm, const int32_t* seg_key,
+                  const int32_t* seg_off, const int32_t* n_seg, int64_t n_seg_max, float* dW, float* db, void* stream);
+/* out[d] = sum_e g[e]*scale*Q[e][d], d < width (row stride ld): gradient of a one-row weight (the affine layer) and
+ * of the GMF column scale. Deterministic two-stage. scratch >= dmt_weighted_colsum_scratch_floats(width). */
+int64_t dmt_weighted_colsum_scratch_floats(int width);
+int dmt_weighted_colsum(const float* g, float scale, const float* Q, int64_t n, int width, int ld, float* out,
+                        float* scratch, void* stream);
+/* loss_fn on a finished prediction vector (src/models/utils.py:7-14): sums[0] = sum of losses, sums[1] = sum of
+ * dloss/dpred, dpred[e] (may be NULL) = dloss/dpred. scratch >= dmt_mf_scratch_floats(). */
+int dmt_loss_fwd(const float* pred, const float* y, int64_t n, int loss_kind, float* dpred, float* sums,
+                 float* scratch, void* stream);
 
 /* ------------------------------------------------------------------ AAE (src/models/ae.py:98-157) */
 

@@ -31,7 +31,7 @@ def set_cfg(fx):
     return cfg
 
 
-MODULE_CASES = [c for c in cases("model") if "_mf_" in c or "_ae_" in c]
+MODULE_CASES = cases("model")
 
 
 @pytest.mark.parametrize("case", MODULE_CASES)
@@ -43,7 +43,7 @@ def test_module_forward_backward(dropin, case):
     if m["model_name"] == "ae":
         model = models.ae(m["enc_users"], m["enc_items"], m["dec_users"], m["dec_items"])
     else:
-        model = models.mf(m["n_users"], m["n_items"])
+        model = getattr(models, m["model_name"])(m["n_users"], m["n_items"])
     model.load_state_dict(fx.group("sd0"))
     model = model.cuda()
     for j in (0, 1):
@@ -82,7 +82,7 @@ def test_module_with_torch_optimizer(dropin, case):
     if m["model_name"] == "ae":
         model = models.ae(m["enc_users"], m["enc_items"], m["dec_users"], m["dec_items"])
     else:
-        model = models.mf(m["n_users"], m["n_items"])
+        model = getattr(models, m["model_name"])(m["n_users"], m["n_items"])
     model.load_state_dict(fx.group("sd0"))
     model = model.cuda()
     model.train(True)

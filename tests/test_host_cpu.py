@@ -1,0 +1,159 @@
+"""CPU-side checks (run with -m "not gpu"): the C-ABI library loads and exports every declared symbol, the
+reference-vocabulary config, synthetic data, epoch layouts, and the organization sharding / exchange on 2 gloo ranks."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import build, native
+
+    path = build.build_native()
+    lib = native.load()  # ctypes declares every entry point: a missing one raises AttributeError here
+    with open(os.path.join(ROOT, "include", "dmt_b200.h")) as f:
+        declared = set(re.findall(r"\b(dmt_[a-z0-9_]+)\s*\(", f.read()))
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (dmt_[a-z0-9_]+)", out))
+    assert declared and declared <= exported, sorted(declared - exported)
+    assert lib.dmt_version() >= 100
+    # only the CUDA runtime/driver and libc: no torch, no python in the boundary library
+    ldd = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "python" not in ldd
+
+
+def test_sass_is_sm100a_only():
+    from dmtcdr_b200 import build
+
+    out = subprocess.run(["cuobjdump", "-lelf", build.build_native()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_path():
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import native
+
+    with pytest.raises(native.NativeError):
+        native.ptr(torch.zeros(3))
+
+
+def test_make_cfg_matches_reference_tables():
+    from dmtcdr_b200.config import make_cfg
+
+    c = make_cfg("ML1M_user_explicit_ae_0_genre_assist_constant-0.1_constant", install=False)
+    assert c["num_organizations"] == 18 and c["local"]["batch_size"]["train"] == 500
+    assert c["local"]["num_epochs"] == 20 and c["global"]["num_epochs"] == 10
+    assert c["assist"]["ar_mode"] == "constant" and c["assist"]["ar"] == 0.1 and "cs" not in c and "pl" not in c
+    c = make_cfg("Amazon_user_implicit_ae_0_genre_assist_constant-0.1_optim_0.5_dp-10", install=False)
+    assert c["num_organizations"] == 4 and c["assist"]["aw_mode"] == "optim" and c["assist"]["match_rate"] == 0.5
+    assert c["pl_mode"] == "dp" and c["pl_param"] == 10.0 and "cs" not in c
+    c = make_cfg("Douban_item_explicit_ae_0_random-8_assist_optim-0.3_constant", install=False)
+    assert c["num_organizations"] == 8 and c["local"]["batch_size"]["train"] == 1000
+
+
+def test_synthetic_data_shape_and_split():
+    from dmtcdr_b200 import synth
+
+    d = synth.make_rating_data("tiny-ML100K", seed=0)
+    M, N, nnz, G, P = synth.SHAPES["tiny-ML100K"]
+    assert d.train.shape == (M, N) and d.train.nnz + d.test.nnz == nnz and d.train.nnz == int(nnz * 0.9)
+    assert d.train.multiply(d.test).nnz == 0  # disjoint (user, item) pairs
+    assert d.item_attr.shape == (N, G) and d.user_profile.shape == (M, P)
+    (trd, trt), (ted, tet) = d.split("implicit")
+    assert set(np.unique(trt.data)) <= {0.0, 1.0} and ted is trd
+    d2 = synth.make_rating_data("tiny-ML100K", seed=0)
+    assert (d.train != d2.train).nnz == 0
+
+
+def test_epoch_layouts():
+    from dmtcdr_b200 import engine as E
+
+    rng = np.random.default_rng(0)
+    d_len = rng.integers(0, 3, size=50)
+    t_len = rng.integers(0, 4, size=50)
+    d_len[[3, 4]] = 0
+    t_len[[4]] = 0  # row 4 has nothing: dropped; row 3 has targets only
+    perm = rng.permutation(50)
+    batches = [perm[s:s + 16] for s in range(0, 50, 16)]
+    a = E.EpochLayout(batches, d_len, t_len)
+    b = E.FastEpochLayout(perm, 16, d_len, t_len)
+    assert 4 not in a.rows and 4 not in b.rows and 3 in a.rows
+    assert a.n_t == b.n_t == int(t_len.sum()) and a.n_d == b.n_d == int(d_len.sum())
+    assert list(a.row_off) == list(b.row_off)
+    for k in range(len(batches)):
+        ra = a.rows[a.row_off[k]:a.row_off[k + 1]]
+        rb = b.rows[b.row_off[k]:b.row_off[k + 1]]
+        assert list(ra) == sorted(ra) and sorted(rb) == list(ra)
+    assert a.active == b.active and a.d_per_batch == b.d_per_batch
+
+
+def test_index_batches_consume_rng_like_a_dataloader():
+    from dmtcdr_b200 import engine as E
+
+    torch.manual_seed(3)
+    b1 = E.index_batches(23, 5, True)
+    after = torch.rand(1)
+    torch.manual_seed(3)
+    torch.empty((), dtype=torch.int64).random_()  # base seed of the loader iterator
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())  # RandomSampler's seed
+    g = torch.Generator()
+    g.manual_seed(seed)
+    perm = torch.randperm(23, generator=g).numpy()
+    assert np.array_equal(np.concatenate(b1), perm) and float(after) == float(torch.rand(1))
+
+
+def test_org_blocks_cover_all_organizations():
+    from dmtcdr_b200 import dist as D
+
+    for K, world in [(18, 1), (18, 2), (18, 4), (18, 8), (3, 8), (64, 8)]:
+        seen = []
+        for r in range(world):
+            orgs, c = D.org_block(K, world, r)
+            assert len(orgs) <= c
+            seen += orgs
+        assert seen == list(range(K))
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+import dmtcdr_b200
+from dmtcdr_b200 import dist as D
+rank, world, _ = D.init_from_env(backend="gloo")
+K, nnz = 5, 37
+orgs, chunk = D.org_block(K, world, rank)
+O = {{k: torch.zeros(chunk * world, nnz) for k in ("train", "test")}}
+for k, O_k in O.items():
+    for o in orgs:
+        O_k[o] = torch.arange(nnz, dtype=torch.float32) + 100 * o + (1000 if k == "test" else 0)
+D.exchange_outputs(O, chunk, rank, world)
+for k, O_k in O.items():
+    for o in range(K):
+        want = torch.arange(nnz, dtype=torch.float32) + 100 * o + (1000 if k == "test" else 0)
+        assert torch.equal(O_k[o], want), (rank, k, o)
+    assert float(O_k[K:].abs().sum()) == 0.0
+assert D.max_over_ranks(float(rank), "cpu") == float(world - 1)
+D.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_exchange_on_two_gloo_ranks(tmp_path):
+    """N>1 path on CPU: the in-place all-gather of organization outputs, world_size 2, gloo."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

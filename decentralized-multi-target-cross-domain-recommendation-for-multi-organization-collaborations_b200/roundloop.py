@@ -116,6 +116,14 @@ class AssistRounds:
     # ------------------------------------------------------------------ one assistance round
     def run_round(self, t, exchange=None):
         """make_dataset -> local training of this rank's organizations -> predict -> exchange -> update."""
+        self.train_predict(t)
+        if exchange is not None:
+            exchange(self.state.O)
+        return self.combine()
+
+    def train_predict(self, t):
+        """Rank-local part of a round. Parameter init, sampler permutations and the dropout stream are seeded per
+        (seed, organization, round), so the result does not depend on how organizations are sharded over ranks."""
         st = self.state
         for k in self.splits:
             st.residual(self.F[k], k, self.clamp, out=self.residual[k])
@@ -123,6 +131,8 @@ class AssistRounds:
         layouts, rows_dev, off_dev = {}, {}, {}
         for org in self.my_orgs:
             eng = self.eng[org]
+            self.gen.manual_seed(E.he_seed(self.seed, org, t, 1 << 20) & (2 ** 63 - 1))
+            self.host_gen.manual_seed(E.he_seed(self.seed, org, t, 1 << 21) & (2 ** 63 - 1))
             flat0 = init_flat_params(eng.n_enc, eng.n_dec, self.H1, self.H2, self.device, self.gen)
             eng.set_round(flat0, self.residual["train"])
             lays = [E.FastEpochLayout(torch.randperm(self.n_rows, generator=self.host_gen).numpy(), self.batch_rows,
@@ -155,11 +165,12 @@ class AssistRounds:
             eng.predict(self.org_test_data[org], st.y["test"], st.O["test"][org])
         for org in self.my_orgs:
             self.eng[org].h.signal_current()  # the current stream waits for every organization's stream
-        if exchange is not None:
-            exchange(st.O)
-        F_next, fitted = st.update(self.F, self.ar, self.ar_mode, self.aw_mode, self.match_rate)
-        self.F = F_next
         self.round_losses[t] = loss_bufs
+
+    def combine(self):
+        """Replicated part: Assist.update over the exchanged outputs -> F_t on every rank."""
+        F_next, fitted = self.state.update(self.F, self.ar, self.ar_mode, self.aw_mode, self.match_rate)
+        self.F = F_next
         return F_next, fitted
 
     def sync(self):

@@ -1,0 +1,57 @@
+"""Organization sharding: the org-sharded round equals the single-rank round.
+
+Two ranks are emulated on ONE GPU, sequentially (no kernels wait on each other): each emulated rank trains and
+predicts only its own block of organizations, the exchange is emulated by copying the rows a real all-gather would
+deliver, then both run the replicated update. F_t must be IDENTICAL to the single-rank run (same kernels, same
+per-organization seeds, same summation order) — bit-for-bit, not just within tolerance.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_emulated_ranks_match_one():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import roundloop, runner, synth
+    from dmtcdr_b200.config import make_cfg
+
+    control = "Amazon_user_implicit_ae_0_genre_assist_constant-0.1_constant"
+    make_cfg(control, device="cuda", seed=0)
+    data = synth.make_rating_data("tiny-Amazon", seed=0)
+    torch.manual_seed(0)
+    dataset = runner.fetch_dataset(data)
+    runner.process_dataset(dataset)
+    split = [s.numpy() for s in runner.split_dataset(dataset)]
+    mats = {k: (dataset[k].data, dataset[k].target) for k in dataset}
+    kw = dict(target_mode="implicit", batch_rows=50, clamp=True, ar=0.1, local_epochs=2, device="cuda:0", seed=3)
+    one = roundloop.AssistRounds(mats, split, rank=0, world=1, **kw)
+    ranks = [roundloop.AssistRounds(mats, split, rank=r, world=2, **kw) for r in (0, 1)]
+    assert sorted(ranks[0].my_orgs + ranks[1].my_orgs) == list(range(len(split)))
+    for r in [one] + ranks:
+        r.round0()
+    for k in ("train", "test"):
+        assert torch.equal(one.F[k], ranks[0].F[k]) and torch.equal(one.F[k], ranks[1].F[k])
+    for t in (1, 2):
+        one.run_round(t)
+        for r in ranks:
+            r.train_predict(t)
+        for r in ranks:
+            r.sync()
+        # what dist.exchange_outputs (in-place all-gather of equal row blocks) delivers
+        for k in ("train", "test"):
+            c = ranks[0].chunk
+            for src in (0, 1):
+                dst = ranks[1 - src]
+                dst.state.O_full[k][src * c:(src + 1) * c].copy_(ranks[src].state.O_full[k][src * c:(src + 1) * c])
+        for r in ranks:
+            r.combine()
+        one.sync()
+        for k in ("train", "test"):
+            assert torch.equal(one.state.O[k], ranks[0].state.O[k])
+            assert torch.equal(one.F[k], ranks[0].F[k]) and torch.equal(one.F[k], ranks[1].F[k])
+            assert torch.isfinite(one.F[k]).all()
+    for r in [one] + ranks:
+        r.close()

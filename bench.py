@@ -163,6 +163,8 @@ def run_reference_arm(args):
 def run_ours(args):
     from dmtcdr_b200 import dist as D
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would break the one-JSON-line contract
     rank, world, local = D.init_from_env()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -231,15 +233,22 @@ def run_ours(args):
                 "adam_GBps": n_params * 28 / (prof["clip_adam"] * 1e-3) / 1e9}
         roof["hbm_case"] = hbm_bound_case(dev, hbm)
 
-    # ---- end to end through the drop-in API with host buffers
-    e2e = None
-    if world == 1 or True:
-        e2e = run_e2e(args, data, rank, world, dev)
+    # ---- end to end through the drop-in API with host buffers (single-process API: measured on rank 0's GPU)
+    e2e = run_e2e(args, data, rank, world, dev)
 
+    if world > 1:
+        D.barrier()
+        import torch.distributed as tdist
+        tdist.destroy_process_group()
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    v, dt = cpu_round_sample(mats, data_split, 1, 20, threads=threads)
+    cpu = None
+    if world == 1:  # the CPU baseline is reported on rank 0 at N=1 only
+        v, dt = cpu_round_sample(mats, data_split, 1, 20, threads=threads)
+        cpu = {"value": v / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "1 of 18 organizations x all 20 local epochs + its predict + residual/update for all "
+                         "organizations ({:.1f} s of CPU work; oracle/ torch-CPU port of the reference)".format(dt)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -248,10 +257,8 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2: per-round working set (18 x 17 MB parameters+moments, "
                                     "2 x 72 MB prediction matrices, plans) exceeds 126 MB"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
-            "cpu_baseline": {"value": v / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "1 of 18 organizations x all 20 local epochs + its predict + residual/update "
-                                       "for all organizations ({:.1f} s of CPU work)".format(dt)}}
-    print(json.dumps(line))
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
 
 
 def hbm_bound_case(dev, hbm):
@@ -323,7 +330,7 @@ def run_e2e(args, data, rank, world, dev):
     return {"value": visits / sec, "unit": UNIT, "ms_per_step": 1e3 * sec,
             "h2d_bytes_per_step": int(E.XFER["h2d"] / n_steps), "d2h_bytes_per_step": int(E.XFER["d2h"] / n_steps),
             "api": "Assist.make_dataset / Organization.train / Organization.predict / Assist.update + test metrics, "
-                   "host scipy CSR in and out", "rmse_last_round": res["metrics"][n_warm + n_steps].get("test/RMSE")}
+                   "host scipy CSR in and out", "n_gpus_used": 1, "rmse_last_round": res["metrics"][n_warm + n_steps].get("test/RMSE")}
 
 
 def main():

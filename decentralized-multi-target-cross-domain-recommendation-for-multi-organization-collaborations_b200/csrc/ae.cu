@@ -9,7 +9,7 @@
 namespace dmt {
 
 // One block per batch row, one thread per hidden unit.
-__global__ void __launch_bounds__(512) ae_encoder_fwd_kernel(const int32_t* __restrict__ rows,
+__device__ __forceinline__ void ae_encoder_fwd_body(const int32_t* __restrict__ rows,
                                                             const int32_t* __restrict__ indptr,
                                                             const int32_t* __restrict__ indices,
                                                             const float* __restrict__ val,
@@ -38,6 +38,18 @@ __global__ void __launch_bounds__(512) ae_encoder_fwd_kernel(const int32_t* __re
         for (; e < e1; ++e) acc = fmaf(val[e], W1t[(int64_t)indices[e] * H + h], acc);
         A1[(int64_t)j * H + h] = tanhf(acc + b1[h]);
     }
+}
+
+__global__ void __launch_bounds__(512) ae_encoder_fwd_kernel(const int32_t* rows, const int32_t* indptr,
+                                                            const int32_t* indices, const float* val,
+                                                            const float* W1t, const float* b1, int H, float* A1,
+                                                            BatchRef br) {
+    ae_encoder_fwd_body(rows, indptr, indices, val, W1t, b1, H, A1, br);
+}
+__global__ void __launch_bounds__(512) ae_encoder_fwd_group(const OrgDev* __restrict__ orgs, int b, int H) {
+    const OrgDev& o = orgs[blockIdx.z];
+    ae_encoder_fwd_body(o.rows, o.d_indptr, o.d_indices, o.d_val, o.P + o.oW1, o.P + o.ob1, H, o.a1,
+                        BatchRef{o.row_off, o.active, b, 0, 0});
 }
 
 // One block (8 warps) per batch row. VEC = H / 128: each lane owns VEC float4 slices of the hidden vector.
@@ -202,7 +214,7 @@ int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int3
 // over ~16 blocks instead of serialising one. Each block leaves a partial dZ3 row; the finish kernel adds a row's
 // partials in chunk order (deterministic) and applies the tanh derivative.
 template <int VEC>
-__global__ void __launch_bounds__(256) ae_decoder_chunk_kernel(const int32_t* __restrict__ rows,
+__device__ __forceinline__ void ae_decoder_chunk_body(const int32_t* __restrict__ rows,
                                                               const int32_t* __restrict__ indptr,
                                                               const int32_t* __restrict__ indices,
                                                               const float* __restrict__ target,
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(256) ae_decoder_chunk_kernel(const int32_t* __
     }
 }
 
-__global__ void __launch_bounds__(256) ae_decoder_finish_kernel(const float* __restrict__ A3, int H, DecChunks dc,
+__device__ __forceinline__ void ae_decoder_finish_body(const float* __restrict__ A3, int H, DecChunks dc,
                                                                 float* __restrict__ dZ3, float* __restrict__ loss_rows,
                                                                 BatchRef br) {
     int lo, hi;
@@ -343,6 +355,53 @@ __global__ void __launch_bounds__(256) ae_decoder_finish_kernel(const float* __r
         for (int c = c0; c < c1; ++c) l += dc.loss_part[c];
         loss_rows[jl] = l;
     }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) ae_decoder_chunk_kernel(const int32_t* rows, const int32_t* indptr,
+                                                              const int32_t* indices, const float* target,
+                                                              const float* A3, const float* W4, const float* b4,
+                                                              int loss_kind, const int32_t* n_targets,
+                                                              const int32_t* ent_off, DecChunks dc, float* gout,
+                                                              BatchRef br) {
+    ae_decoder_chunk_body<VEC>(rows, indptr, indices, target, A3, W4, b4, loss_kind, n_targets, ent_off, dc, gout, br);
+}
+__global__ void __launch_bounds__(256) ae_decoder_finish_kernel(const float* A3, int H, DecChunks dc, float* dZ3,
+                                                                float* loss_rows, BatchRef br) {
+    ae_decoder_finish_body(A3, H, dc, dZ3, loss_rows, br);
+}
+template <int VEC>
+__global__ void __launch_bounds__(256) ae_decoder_chunk_group(const OrgDev* __restrict__ orgs, int b) {
+    const OrgDev& o = orgs[blockIdx.z];
+    ae_decoder_chunk_body<VEC>(o.rows, o.t_indptr, o.t_indices, o.t_val, o.a3, o.P + o.oW4, o.P + o.ob4, DMT_LOSS_MSE,
+                               o.t_batch_cnt, o.t_ent_off, o.dc, o.gbuf, BatchRef{o.row_off, o.active, b, 0, 0});
+}
+__global__ void __launch_bounds__(256) ae_decoder_finish_group(const OrgDev* __restrict__ orgs, int b, int H) {
+    const OrgDev& o = orgs[blockIdx.z];
+    ae_decoder_finish_body(o.a3, H, o.dc, o.dz3, o.loss_rows, BatchRef{o.row_off, o.active, b, 0, 0});
+}
+
+int launch_group_encoder(const OrgDev* orgs, int G, int b, int B, int H1, cudaStream_t st) {
+    int threads = H1 >= 512 ? 512 : (H1 + 31) / 32 * 32;
+    ae_encoder_fwd_group<<<dim3(B, 1, G), threads, 0, st>>>(orgs, b, H1);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_group_decoder(const OrgDev* orgs, int G, int b, int B, int H1, cudaStream_t st) {
+    // chunks of all organizations share the persistent grid: x = chunk slots per organization, z = organization
+    int per_org = (kNumSMs * 8 + G - 1) / G;
+    if (per_org < 8) per_org = 8;
+    dim3 grid(per_org, 1, G);
+    if (H1 == 128) ae_decoder_chunk_group<1><<<grid, 256, 0, st>>>(orgs, b);
+    else if (H1 == 256) ae_decoder_chunk_group<2><<<grid, 256, 0, st>>>(orgs, b);
+    else if (H1 == 384) ae_decoder_chunk_group<3><<<grid, 256, 0, st>>>(orgs, b);
+    else if (H1 == 512) ae_decoder_chunk_group<4><<<grid, 256, 0, st>>>(orgs, b);
+    else { set_error("decoder hidden size must be 128, 256, 384 or 512"); return DMT_E_ARG; }
+    DMT_LAUNCH_CHECK();
+    ae_decoder_finish_group<<<dim3(B, 1, G), 256, 0, st>>>(orgs, b, H1);
+    DMT_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,

@@ -12,7 +12,7 @@ constexpr int BK = 32;
 // Global -> register prefetch of k-tile t+1 overlaps the FFMA loop on k-tile t (double-buffered shared memory, one
 // barrier per k-tile): these GEMMs are tiny (M = one 500-row batch), so latency, not bandwidth, is what is hidden.
 template <int BM, int BN, bool A_KMAJOR, bool B_KMAJOR, int DYN /*0: M dynamic, 1: K dynamic*/, class Epi>
-__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, int M,
+__device__ __forceinline__ void sgemm_body(const float* __restrict__ A, const float* __restrict__ B, int M,
                                                     int N, int K, int lda, int ldb, Epi epi, BatchRef br, int zK) {
     constexpr int TM = BM / 16, TN = BN / 16;
     constexpr int LA = BM * BK / 256, LB = BN * BK / 256;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 
 // db[n] = sum over the batch rows of dY[:, n]. 32 columns x 32 row-lanes per block: the row loop is 32x shorter than
 // the batch (latency, not bandwidth, is what this tiny reduction costs).
-__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ dY, int n, float* __restrict__ db,
+__device__ __forceinline__ void colsum_body(const float* __restrict__ dY, int n, float* __restrict__ db,
                                                       BatchRef br) {
     __shared__ float sh[32][33];
     int lo, hi;
@@ -188,6 +188,91 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
         for (int i = 0; i < 32; ++i) t += sh[i][x];
         db[col] = t;
     }
+}
+
+template <int BM, int BN, bool A_KMAJOR, bool B_KMAJOR, int DYN, class Epi>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* A, const float* B, int M, int N, int K, int lda,
+                                                    int ldb, Epi epi, BatchRef br, int zK) {
+    sgemm_body<BM, BN, A_KMAJOR, B_KMAJOR, DYN, Epi>(A, B, M, N, K, lda, ldb, epi, br, zK);
+}
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* dY, int n, float* db, BatchRef br) {
+    colsum_body(dY, n, db, br);
+}
+
+// Group forms (z = organization). `which`: 0 a2/c = tanh(a1 W2^T + b2) with dropout, 1 a3 = tanh(c W3^T + b3),
+// 2 dW3 = dz3^T c, 3 dz2 = (dz3 W3) * drop * (1-a2^2), 4 dW2 = dz2^T a1, 5 dz1 = (dz2 W2) * (1-a1^2)
+__device__ __forceinline__ Dropout group_dropout(const OrgDev& o, int b) {
+    Dropout d;
+    d.seed_dev = o.seed_dev;
+    d.step_dev = o.step_dev;
+    d.row_base = o.row_off;
+    d.b = b;
+    d.scale = 2.0f;  // nn.Dropout(p=0.5), reference src/models/ae.py:81
+    d.p = 0.5f;
+    d.enabled = 1;
+    return d;
+}
+template <int WHICH, int BM, int BN>
+__global__ void __launch_bounds__(256) dense_group(const OrgDev* __restrict__ orgs, int b, int B, int H1, int H2) {
+    const OrgDev& o = orgs[blockIdx.z];
+    const BatchRef br{o.row_off, o.active, b, 0, 0};
+    float *W2 = o.P + o.oW2, *b2 = o.P + o.ob2, *W3 = o.P + o.oW3, *b3 = o.P + o.ob3;
+    if (WHICH == 0) {
+        FwdEpi epi{b2, o.c, o.a2, group_dropout(o, b), H2, 1};
+        sgemm_body<BM, BN, true, true, 0>(o.a1, W2, B, H2, H1, H1, H1, epi, br, 0);
+    } else if (WHICH == 1) {
+        FwdEpi epi{b3, o.a3, nullptr, Dropout(), H1, 1};
+        sgemm_body<BM, BN, true, true, 0>(o.c, W3, B, H1, H2, H2, H2, epi, br, 0);
+    } else if (WHICH == 2) {
+        StoreEpi epi{o.G + o.oW3, H2, 0};
+        sgemm_body<BM, BN, false, false, 1>(o.dz3, o.c, H1, H2, B, H1, H2, epi, br, 0);
+    } else if (WHICH == 3) {
+        BwdXEpi epi{o.a2, o.dz2, group_dropout(o, b), H2, 1};
+        sgemm_body<BM, BN, true, false, 0>(o.dz3, W3, B, H2, H1, H1, H2, epi, br, 0);
+    } else if (WHICH == 4) {
+        StoreEpi epi{o.G + o.oW2, H1, 0};
+        sgemm_body<BM, BN, false, false, 1>(o.dz2, o.a1, H2, H1, B, H2, H1, epi, br, 0);
+    } else {
+        BwdXEpi epi{o.a1, o.dz1, Dropout(), H1, 1};
+        sgemm_body<BM, BN, true, false, 0>(o.dz2, W2, B, H1, H2, H2, H1, epi, br, 0);
+    }
+}
+// column sums: which 2 -> db3 from dz3 [H1], 4 -> db2 from dz2 [H2], 6 -> db1 from dz1 [H1]
+__global__ void __launch_bounds__(1024) colsum_group(const OrgDev* __restrict__ orgs, int b, int which, int n) {
+    const OrgDev& o = orgs[blockIdx.z];
+    const float* src = which == 2 ? o.dz3 : (which == 4 ? o.dz2 : o.dz1);
+    float* dst = o.G + (which == 2 ? o.ob3 : (which == 4 ? o.ob2 : o.ob1));
+    colsum_body(src, n, dst, BatchRef{o.row_off, o.active, b, 0, 0});
+}
+
+int launch_group_dense(const OrgDev* orgs, int G, int b, int B, int H1, int H2, int which, cudaStream_t st) {
+    // output shapes: 0 [B x H2], 1 [B x H1], 2 [H1 x H2], 3 [B x H2], 4 [H2 x H1], 5 [B x H1]
+    const int M = (which == 2) ? H1 : (which == 4 ? H2 : B);
+    const int N = (which == 0 || which == 3 || which == 2) ? H2 : H1;
+    dim3 grid((N + 63) / 64, (M + 63) / 64, G);  // 64x64 tiles: with G organizations per launch the grid is wide enough
+#define DMT_DG(W) dense_group<W, 64, 64><<<grid, 256, 0, st>>>(orgs, b, B, H1, H2)
+    switch (which) {
+        case 0: DMT_DG(0); break;
+        case 1: DMT_DG(1); break;
+        case 2: DMT_DG(2); break;
+        case 3: DMT_DG(3); break;
+        case 4: DMT_DG(4); break;
+        default: DMT_DG(5); break;
+    }
+#undef DMT_DG
+    DMT_LAUNCH_CHECK();
+    if (which == 2 || which == 4) {
+        int n = which == 2 ? H1 : H2;
+        colsum_group<<<dim3((n + 31) / 32, 1, G), 1024, 0, st>>>(orgs, b, which, n);
+        DMT_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int launch_group_colsum_dz1(const OrgDev* orgs, int G, int b, int H1, cudaStream_t st) {
+    colsum_group<<<dim3((H1 + 31) / 32, 1, G), 1024, 0, st>>>(orgs, b, 6, H1);
+    DMT_LAUNCH_CHECK();
+    return 0;
 }
 
 template <bool AK, bool BKM, int DYN, class Epi>

@@ -12,7 +12,9 @@
 // 148 SMs even though a single 500-row batch cannot.
 #include <cub/cub.cuh>
 
+#include <cstring>
 #include <new>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -102,10 +104,11 @@ static int dalloc(T** p, int64_t n) {
     return 0;
 }
 
-static int alloc_side(PlanSide& s, int64_t cap, int rows_cap, int nb_cap, int n_cols, int H) {
+static int alloc_side(PlanSide& s, int64_t cap, int rows_cap, int nb_cap, int n_cols, int H, int batch_rows) {
     s.cap = cap;
     s.chunk_cap = cap + cap / kSegChunk + 16;
-    s.part_rows = (int64_t)n_cols + cap / kSegChunk + 16;
+    int64_t per_batch = (int64_t)batch_rows * n_cols < cap ? (int64_t)batch_rows * n_cols : cap;  // entries of one batch
+    s.part_rows = (int64_t)n_cols + per_batch / kSegChunk + 16;
     int rc = 0;
     if ((rc = dalloc(&s.n_ch, cap + 2))) return rc;
     if ((rc = dalloc(&s.seg_chunk_off, cap + 2))) return rc;
@@ -232,25 +235,24 @@ static int bits_for(int64_t bound) {
     return bits;
 }
 
-static int scan_lengths(dmt_org* o, PlanSide& s, int n) {
+static int scan_lengths(dmt_org* o, PlanSide& s, int n, cudaStream_t st) {
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, s.len, s.ent_off, n + 1);
     if ((int64_t)bytes > o->sort_temp_bytes) {
         set_error("plan: scan temp too small");
         return DMT_E_STATE;
     }
-    DMT_CUDA(cub::DeviceScan::ExclusiveSum(o->sort_temp, bytes, s.len, s.ent_off, n + 1, o->st));
+    DMT_CUDA(cub::DeviceScan::ExclusiveSum(o->sort_temp, bytes, s.len, s.ent_off, n + 1, st));
     return 0;
 }
 
-static int build_plan(dmt_org* o, int n, int nb, int64_t n_t, int64_t n_d) {
-    cudaStream_t st = o->st;
+static int build_plan(dmt_org* o, int n, int nb, int64_t n_t, int64_t n_d, cudaStream_t st) {
     plan_row_len_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(o->rows_buf, o->row_off_buf, nb, n, o->t_indptr,
                                                             o->d_indptr, o->pt.len, o->pd.len, o->row_batch);
     DMT_LAUNCH_CHECK();
     int rc;
-    if ((rc = scan_lengths(o, o->pt, n))) return rc;
-    if ((rc = scan_lengths(o, o->pd, n))) return rc;
+    if ((rc = scan_lengths(o, o->pt, n, st))) return rc;
+    if ((rc = scan_lengths(o, o->pd, n, st))) return rc;
     plan_batch_meta_kernel<<<(nb + 127) / 128, 128, 0, st>>>(o->row_off_buf, nb, o->pt.ent_off, o->pd.ent_off,
                                                             o->pt.batch_cnt, o->pd.batch_cnt, o->active);
     DMT_LAUNCH_CHECK();
@@ -417,7 +419,8 @@ extern "C" {
 
 int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, int H2, const int32_t* d_indptr,
                    const int32_t* d_indices, const float* d_val, int64_t d_nnz, const int32_t* t_indptr,
-                   const int32_t* t_indices, int64_t t_nnz, int batch_rows, int loss_kind, void* stream) {
+                   const int32_t* t_indices, int64_t t_nnz, int batch_rows, int loss_kind, int plan_epochs,
+                   void* stream) {
     DMT_REQUIRE(out && n_rows > 0 && n_enc > 0 && n_dec > 0 && batch_rows > 0, "dmt_org_create: bad sizes");
     DMT_REQUIRE(H1 % 128 == 0 && H1 <= 512 && H2 > 0, "dmt_org_create: H1 must be 128/256/384/512");
     DMT_REQUIRE(d_nnz >= 0 && t_nnz >= 0 && t_nnz < (1LL << 31) - 2 && d_nnz < (1LL << 31) - 2,
@@ -451,8 +454,13 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     o->n_params = off;
     o->act_rows = n_rows < 65536 ? n_rows : 65536;
     if (o->act_rows < batch_rows) o->act_rows = batch_rows;
-    o->rows_cap = n_rows;
-    o->nb_cap = (n_rows + batch_rows - 1) / batch_rows + 1;
+    // one plan / one graph may cover several local epochs at once (plan_epochs): the plan buffers are sized for it
+    if (plan_epochs < 1) plan_epochs = 1;
+    DMT_REQUIRE((int64_t)t_nnz * plan_epochs < (1LL << 31) - 2 && (int64_t)d_nnz * plan_epochs < (1LL << 31) - 2,
+                "dmt_org_create: plan_epochs x nnz must fit int32");
+    const int64_t t_cap = t_nnz * plan_epochs, d_cap = d_nnz * plan_epochs;
+    o->rows_cap = n_rows * plan_epochs;
+    o->nb_cap = ((n_rows + batch_rows - 1) / batch_rows + 1) * plan_epochs;
 #define A(expr) if ((rc = (expr))) { free_all(o); delete o; return rc; }
     A(dalloc(&o->P, o->n_params)); A(dalloc(&o->G, o->n_params)); A(dalloc(&o->M, o->n_params));
     A(dalloc(&o->V, o->n_params));
@@ -461,16 +469,19 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     A(dalloc(&o->dz3, (int64_t)batch_rows * H1)); A(dalloc(&o->dz2, (int64_t)batch_rows * H2));
     A(dalloc(&o->dz1, (int64_t)batch_rows * H1)); A(dalloc(&o->loss_rows, batch_rows));
     A(dalloc(&o->iota_rows, n_rows));
-    A(alloc_side(o->pt, t_nnz, o->rows_cap, o->nb_cap, n_dec, H1));
-    A(alloc_side(o->pd, d_nnz, o->rows_cap, o->nb_cap, n_enc, H1));
-    o->dec_chunk_cap = t_nnz / kDecChunk + o->rows_cap + 16;
-    o->dec_part_rows = t_nnz / kDecChunk + batch_rows + 16;
+    A(alloc_side(o->pt, t_cap, o->rows_cap, o->nb_cap, n_dec, H1, batch_rows));
+    A(alloc_side(o->pd, d_cap, o->rows_cap, o->nb_cap, n_enc, H1, batch_rows));
+    o->dec_chunk_cap = t_cap / kDecChunk + o->rows_cap + 16;
+    {
+        int64_t per_batch = (int64_t)batch_rows * n_dec < t_cap ? (int64_t)batch_rows * n_dec : t_cap;
+        o->dec_part_rows = per_batch / kDecChunk + batch_rows + 16;
+    }
     A(dalloc(&o->t_nch_row, o->rows_cap + 2)); A(dalloc(&o->t_chunk_off, o->rows_cap + 2));
     A(dalloc(&o->t_chunk_row, o->dec_chunk_cap)); A(dalloc(&o->t_batch_chunk, o->nb_cap + 2));
     A(dalloc(&o->dz_part, o->dec_part_rows * H1)); A(dalloc(&o->loss_part, o->dec_part_rows));
-    A(dalloc(&o->gbuf, t_nnz)); A(dalloc(&o->dval_ord, d_nnz)); A(dalloc(&o->row_batch, o->rows_cap + 1));
+    A(dalloc(&o->gbuf, t_cap)); A(dalloc(&o->dval_ord, d_cap)); A(dalloc(&o->row_batch, o->rows_cap + 1));
     A(dalloc(&o->active, o->nb_cap + 1));
-    o->sort_temp_bytes = sort_segments_temp_bytes(t_nnz > d_nnz ? t_nnz : d_nnz);
+    o->sort_temp_bytes = sort_segments_temp_bytes(t_cap > d_cap ? t_cap : d_cap);
     if (o->sort_temp_bytes < (1 << 20)) o->sort_temp_bytes = 1 << 20;
     A(dalloc(reinterpret_cast<char**>(&o->sort_temp), o->sort_temp_bytes));
     A(dalloc(&o->rows_buf, o->rows_cap)); A(dalloc(&o->row_off_buf, o->nb_cap + 1));
@@ -557,7 +568,7 @@ int dmt_org_train_epoch(dmt_org_t* o, const int32_t* rows, const int32_t* row_of
         cudaGraph_t graph = nullptr;
         DMT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         long long before = launch_count();
-        rc = build_plan(o, n_rows_total, n_batches, n_t_entries, n_d_entries);
+        rc = build_plan(o, n_rows_total, n_batches, n_t_entries, n_d_entries, st);
         for (int b = 0; b < n_batches && rc == 0; ++b) rc = enqueue_step(o, b, use_keep != 0, hp);
         o->g_kernels = launch_count() - before;
         count_launch(-o->g_kernels);  // captured, not executed: counted at every cudaGraphLaunch instead
@@ -666,6 +677,190 @@ int dmt_org_signal_stream(dmt_org_t* o, void* stream) {
     if (as_stream(stream) == o->st) return 0;
     DMT_CUDA(cudaEventRecord(o->ev, o->st));
     DMT_CUDA(cudaStreamWaitEvent(as_stream(stream), o->ev, 0));
+    return 0;
+}
+
+
+/* ---------------------------------------------------------------- organization groups */
+
+struct dmt_group {
+    std::vector<dmt_org*> orgs;
+    std::vector<OrgDev> views;  // what d_orgs currently holds
+    OrgDev* d_orgs;
+    cudaStream_t st;
+    cudaEvent_t ev;
+    cudaGraphExec_t exec;
+    long long g_kernels;
+    int g_nb;
+    AdamHyper g_hp;
+    int64_t n_params_max;
+    int n_enc_max;
+};
+
+static OrgDev org_view(dmt_org* o) {
+    OrgDev v{};
+    v.rows = o->rows_buf; v.row_off = o->row_off_buf; v.active = o->active;
+    v.d_indptr = o->d_indptr; v.d_indices = o->d_indices; v.t_indptr = o->t_indptr; v.t_indices = o->t_indices;
+    v.d_val = o->d_val; v.t_val = o->t_val;
+    v.P = o->P; v.G = o->G; v.M = o->M; v.V = o->V; v.n_params = o->n_params;
+    v.oW1 = o->oW1; v.ob1 = o->ob1; v.oW2 = o->oW2; v.ob2 = o->ob2; v.oW3 = o->oW3; v.ob3 = o->ob3;
+    v.oW4 = o->oW4; v.ob4 = o->ob4; v.n_enc = o->n_enc; v.n_dec = o->n_dec;
+    v.a1 = o->a1; v.a2 = o->a2; v.c = o->c; v.a3 = o->a3; v.dz3 = o->dz3; v.dz2 = o->dz2; v.dz1 = o->dz1;
+    v.loss_rows = o->loss_rows;
+    v.t_ent_off = o->pt.ent_off; v.t_batch_cnt = o->pt.batch_cnt;
+    v.dc = DecChunks{o->t_chunk_off, o->t_chunk_row, o->t_batch_chunk, o->dz_part, o->loss_part};
+    v.gbuf = o->gbuf;
+    v.seg_t = ChunkedSegs{o->pt.perm, o->pt.ent_row, o->pt.seg_key, o->pt.seg_off, o->pt.batch_seg_off,
+                          o->pt.seg_chunk_off, o->pt.chunk_seg, o->pt.batch_chunk_off, o->pt.part, o->pt.part_bias, 0,
+                          o->n_dec};
+    v.seg_d = ChunkedSegs{o->pd.perm, o->pd.ent_row, o->pd.seg_key, o->pd.seg_off, o->pd.batch_seg_off,
+                          o->pd.seg_chunk_off, o->pd.chunk_seg, o->pd.batch_chunk_off, o->pd.part, o->pd.part_bias, 0,
+                          o->n_enc};
+    v.dval_ord = o->dval_ord;
+    v.partial = o->partial; v.sc = o->sc; v.step_dev = o->step_dev; v.loss_buf = o->loss_buf; v.seed_dev = o->seed_dev;
+    return v;
+}
+
+// The graph only bakes the address of the view array, so new target pointers etc. need no re-capture: the views are
+// re-uploaded whenever they differ from what the device holds.
+static int upload_views(dmt_group* g) {
+    std::vector<OrgDev> host;
+    for (dmt_org* o : g->orgs) host.push_back(org_view(o));
+    if (g->views.size() == host.size() && memcmp(g->views.data(), host.data(), host.size() * sizeof(OrgDev)) == 0)
+        return 0;
+    DMT_CUDA(cudaStreamSynchronize(g->st));  // nothing in flight may still read the old views
+    g->views = host;
+    DMT_CUDA(cudaMemcpy(g->d_orgs, g->views.data(), host.size() * sizeof(OrgDev), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int enqueue_group_step(dmt_group* g, int b, AdamHyper hp) {
+    dmt_org* o0 = g->orgs[0];
+    const int G = (int)g->orgs.size(), B = o0->batch_rows, H1 = o0->H1, H2 = o0->H2;
+    cudaStream_t st = g->st;
+    int rc;
+    if ((rc = launch_group_encoder(g->d_orgs, G, b, B, H1, st))) return rc;
+    if ((rc = launch_group_dense(g->d_orgs, G, b, B, H1, H2, 0, st))) return rc;
+    if ((rc = launch_group_dense(g->d_orgs, G, b, B, H1, H2, 1, st))) return rc;
+    if ((rc = launch_group_decoder(g->d_orgs, G, b, B, H1, st))) return rc;
+    if ((rc = launch_group_segments(g->d_orgs, G, b, 0, o0->n_dec, H1, st))) return rc;
+    if ((rc = launch_group_dense(g->d_orgs, G, b, B, H1, H2, 2, st))) return rc;
+    if ((rc = launch_group_dense(g->d_orgs, G, b, B, H1, H2, 3, st))) return rc;
+    if ((rc = launch_group_dense(g->d_orgs, G, b, B, H1, H2, 4, st))) return rc;
+    if ((rc = launch_group_dense(g->d_orgs, G, b, B, H1, H2, 5, st))) return rc;
+    if ((rc = launch_group_segments(g->d_orgs, G, b, 1, g->n_enc_max, H1, st))) return rc;
+    if ((rc = launch_group_colsum_dz1(g->d_orgs, G, b, H1, st))) return rc;
+    if ((rc = launch_group_optim(g->d_orgs, G, b, g->n_params_max, hp, st))) return rc;
+    return 0;
+}
+
+int dmt_group_create(dmt_group_t** out, dmt_org_t* const* orgs, int n, void* stream) {
+    DMT_REQUIRE(out && orgs && n >= 1, "dmt_group_create: bad argument");
+    dmt_group* g = new (std::nothrow) dmt_group();
+    if (!g) return DMT_E_NOMEM;
+    g->exec = nullptr; g->g_nb = -1; g->d_orgs = nullptr; g->n_params_max = 0; g->n_enc_max = 0;
+    for (int i = 0; i < n; ++i) {
+        dmt_org* o = orgs[i];
+        if (!o || o->n_rows != orgs[0]->n_rows || o->H1 != orgs[0]->H1 || o->H2 != orgs[0]->H2 ||
+            o->batch_rows != orgs[0]->batch_rows || o->n_dec != orgs[0]->n_dec) {
+            delete g;
+            set_error("dmt_group_create: organizations must share rows, hidden sizes, batch size and target width");
+            return DMT_E_ARG;
+        }
+        g->orgs.push_back(o);
+        if (o->n_params > g->n_params_max) g->n_params_max = o->n_params;
+        if (o->n_enc > g->n_enc_max) g->n_enc_max = o->n_enc;
+    }
+    if (stream) g->st = as_stream(stream);
+    else DMT_CUDA(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
+    DMT_CUDA(cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming));
+    DMT_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_orgs), sizeof(OrgDev) * n));
+    *out = g;
+    return 0;
+}
+
+int dmt_group_destroy(dmt_group_t* g) {
+    if (!g) return 0;
+    cudaStreamSynchronize(g->st);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    cudaFree(g->d_orgs);
+    cudaEventDestroy(g->ev);
+    delete g;
+    return 0;
+}
+
+void* dmt_group_stream(dmt_group_t* g) { return g ? (void*)g->st : nullptr; }
+
+int dmt_group_train(dmt_group_t* g, const int32_t* const* rows, const int32_t* const* row_off, int n_rows_total,
+                    int n_batches, const int64_t* n_t_entries, const int64_t* n_d_entries, const uint64_t* seeds,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, float max_norm,
+                    float* const* batch_loss) {
+    DMT_REQUIRE(g && rows && row_off && n_t_entries && n_d_entries && seeds, "dmt_group_train: null");
+    const int G = (int)g->orgs.size();
+    AdamHyper hp{lr, beta1, beta2, eps, weight_decay, max_norm};
+    int rc = 0;
+    // 1. per-organization plans, each on the organization's own stream (they are independent), joined below
+    for (int i = 0; i < G; ++i) {
+        dmt_org* o = g->orgs[i];
+        DMT_REQUIRE(o->t_val != nullptr, "dmt_group_train: call dmt_org_set_target on every organization first");
+        DMT_REQUIRE(n_batches >= 1 && n_batches <= o->nb_cap && n_rows_total <= o->rows_cap &&
+                        n_t_entries[i] <= o->pt.cap && n_d_entries[i] <= o->pd.cap,
+                    "dmt_group_train: over the plan capacity (raise plan_epochs at dmt_org_create)");
+        DMT_REQUIRE((int64_t)n_batches * (o->n_dec > o->n_enc ? o->n_dec : o->n_enc) < (1LL << 32),
+                    "dmt_group_train: batches x columns must fit 32-bit sort keys");
+        cudaStream_t st = o->st;
+        DMT_CUDA(cudaEventRecord(g->ev, g->st));  // order after whatever the caller enqueued on the group stream
+        DMT_CUDA(cudaStreamWaitEvent(st, g->ev, 0));
+        DMT_CUDA(cudaMemcpyAsync(o->rows_buf, rows[i], (size_t)n_rows_total * 4, cudaMemcpyDeviceToDevice, st));
+        DMT_CUDA(cudaMemcpyAsync(o->row_off_buf, row_off[i], (size_t)(n_batches + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        DMT_CUDA(cudaMemcpyAsync(o->seed_dev, &seeds[i], sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if ((rc = build_plan(o, n_rows_total, n_batches, n_t_entries[i], n_d_entries[i], st))) return rc;
+        DMT_CUDA(cudaEventRecord(o->ev, st));
+        DMT_CUDA(cudaStreamWaitEvent(g->st, o->ev, 0));
+    }
+    // 2. one graph for all steps of all organizations
+    if ((rc = upload_views(g))) return rc;
+    bool stale = !g->exec || g->g_nb != n_batches || !same_hp(hp, g->g_hp);
+    if (stale) {
+        if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        DMT_CUDA(cudaStreamBeginCapture(g->st, cudaStreamCaptureModeThreadLocal));
+        long long before = launch_count();
+        for (int b = 0; b < n_batches && rc == 0; ++b) rc = enqueue_group_step(g, b, hp);
+        g->g_kernels = launch_count() - before;
+        count_launch(-g->g_kernels);
+        cudaError_t e = cudaStreamEndCapture(g->st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+        e = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g->exec = nullptr; set_error(cudaGetErrorString(e)); return (int)e; }
+        g->g_nb = n_batches; g->g_hp = hp;
+    }
+    DMT_CUDA(cudaGraphLaunch(g->exec, g->st));
+    count_launch(g->g_kernels);
+    if (batch_loss)
+        for (int i = 0; i < G; ++i)
+            if (batch_loss[i])
+                DMT_CUDA(cudaMemcpyAsync(batch_loss[i], g->orgs[i]->loss_buf, (size_t)n_batches * 4,
+                                         cudaMemcpyDeviceToDevice, g->st));
+    // later per-organization work (predict, get_params) must see the trained parameters
+    DMT_CUDA(cudaEventRecord(g->ev, g->st));
+    for (int i = 0; i < G; ++i) DMT_CUDA(cudaStreamWaitEvent(g->orgs[i]->st, g->ev, 0));
+    return 0;
+}
+
+int dmt_group_sync(dmt_group_t* g) {
+    DMT_REQUIRE(g, "dmt_group_sync: null");
+    DMT_CUDA(cudaStreamSynchronize(g->st));
+    return 0;
+}
+
+int dmt_group_wait_stream(dmt_group_t* g, void* stream) {
+    DMT_REQUIRE(g, "dmt_group_wait_stream: null");
+    if (as_stream(stream) == g->st) return 0;
+    DMT_CUDA(cudaEventRecord(g->ev, as_stream(stream)));
+    DMT_CUDA(cudaStreamWaitEvent(g->st, g->ev, 0));
     return 0;
 }
 

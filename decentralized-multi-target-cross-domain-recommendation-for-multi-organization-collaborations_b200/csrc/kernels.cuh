@@ -49,7 +49,8 @@ __device__ __forceinline__ float dropout_factor(const Dropout& d, int row, int c
     if (d.keep != nullptr) return d.keep[r * ld + col] ? d.scale : 0.f;
     uint64_t seed = d.seed_dev ? *d.seed_dev : 0ull;
     uint64_t t = d.step_dev ? (uint64_t)(*d.step_dev) : 0ull;
-    uint32_t h = mix32(seed ^ (t * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)r << 24) ^ (uint64_t)col);
+    // keyed on (seed, optimizer step, row inside the batch, unit): independent of how batches are packed into plans
+    uint32_t h = mix32(seed ^ (t * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)row << 24) ^ (uint64_t)col);
     return ((h >> 8) * (1.0f / 16777216.0f)) >= d.p ? d.scale : 0.f;
 }
 
@@ -117,6 +118,36 @@ int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const i
                              const float* A3, const float* W4, const float* b4, int H, int loss_kind,
                              const int32_t* n_targets, const int32_t* ent_off, DecChunks dc, float* gout, float* dZ3,
                              float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st);
+
+// ---------------------------------------------------------------- organization groups (one launch = all organizations)
+// Device-visible view of one organization. A group launch adds the organization as grid dimension z, so a step of
+// ALL organizations of a rank is the same ~20 launches as a step of one (the per-organization kernels are far too
+// small to fill 148 SMs, and ~2.7 us of launch processing per kernel node is what bounded the per-org design).
+struct OrgDev {
+    const int32_t *rows, *row_off, *active;
+    const int32_t *d_indptr, *d_indices, *t_indptr, *t_indices;
+    const float *d_val, *t_val;
+    float *P, *G, *M, *V;
+    int64_t n_params, oW1, ob1, oW2, ob2, oW3, ob3, oW4, ob4;
+    int n_enc, n_dec;
+    float *a1, *a2, *c, *a3, *dz3, *dz2, *dz1, *loss_rows;
+    const int32_t *t_ent_off, *t_batch_cnt;
+    DecChunks dc;
+    float* gbuf;
+    ChunkedSegs seg_t, seg_d;  // .b is overwritten per launch
+    const float* dval_ord;
+    float* partial;
+    AdamScalars* sc;
+    int* step_dev;
+    float* loss_buf;
+    const uint64_t* seed_dev;
+};
+int launch_group_encoder(const OrgDev* orgs, int G, int b, int B, int H1, cudaStream_t st);
+int launch_group_dense(const OrgDev* orgs, int G, int b, int B, int H1, int H2, int which, cudaStream_t st);
+int launch_group_decoder(const OrgDev* orgs, int G, int b, int B, int H1, cudaStream_t st);
+int launch_group_segments(const OrgDev* orgs, int G, int b, int side, int n_cols_max, int H1, cudaStream_t st);
+int launch_group_colsum_dz1(const OrgDev* orgs, int G, int b, int H1, cudaStream_t st);
+int launch_group_optim(const OrgDev* orgs, int G, int b, int64_t n_params_max, AdamHyper hp, cudaStream_t st);
 
 int64_t sort_segments_temp_bytes(int64_t n);
 int sort_segments(const uint32_t* keys, int64_t n, int key_bits, int32_t* perm, int32_t* seg_key, int32_t* seg_off,

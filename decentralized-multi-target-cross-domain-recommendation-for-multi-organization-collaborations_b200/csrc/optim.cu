@@ -6,7 +6,7 @@
 
 namespace dmt {
 
-__global__ void __launch_bounds__(256) sqnorm_stage1_kernel(const float* __restrict__ g, int64_t n,
+__device__ __forceinline__ void sqnorm_stage1_body(const float* __restrict__ g, int64_t n,
                                                             float* __restrict__ partial, BatchRef br) {
     __shared__ float sh[32];
     int lo, hi;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) sqnorm_stage1_kernel(const float* __restr
 }
 
 // Finishes the norm, derives the step scalars and (engine mode) reduces the batch loss and advances the step.
-__global__ void adam_prepare_kernel(const float* __restrict__ partial, int n_partial, const float* sqnorm_in,
+__device__ __forceinline__ void adam_prepare_body(const float* __restrict__ partial, int n_partial, const float* sqnorm_in,
                                     float* sqnorm_out, AdamScalars* sc, AdamHyper hp, int64_t step_by_value,
                                     int* step_dev, const float* loss_rows, const int32_t* n_targets_ptr,
                                     float* loss_out, BatchRef br) {
@@ -70,7 +70,7 @@ __global__ void adam_prepare_kernel(const float* __restrict__ partial, int n_par
 }
 
 template <bool ZERO_G>
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float* __restrict__ g,
+__device__ __forceinline__ void adam_body(float* __restrict__ w, float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    const AdamScalars* __restrict__ sc, AdamHyper hp) {
     if (sc->active == 0) return;
@@ -109,6 +109,52 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, float*
         if (ZERO_G) g[i] = 0.f;
     }
     (void)b1;
+}
+
+__global__ void __launch_bounds__(256) sqnorm_stage1_kernel(const float* g, int64_t n, float* partial, BatchRef br) {
+    sqnorm_stage1_body(g, n, partial, br);
+}
+__global__ void adam_prepare_kernel(const float* partial, int n_partial, const float* sqnorm_in, float* sqnorm_out,
+                                    AdamScalars* sc, AdamHyper hp, int64_t step_by_value, int* step_dev,
+                                    const float* loss_rows, const int32_t* n_targets_ptr, float* loss_out,
+                                    BatchRef br) {
+    adam_prepare_body(partial, n_partial, sqnorm_in, sqnorm_out, sc, hp, step_by_value, step_dev, loss_rows,
+                      n_targets_ptr, loss_out, br);
+}
+template <bool ZERO_G>
+__global__ void __launch_bounds__(256) adam_kernel(float* w, float* g, float* m, float* v, int64_t n,
+                                                   const AdamScalars* sc, AdamHyper hp) {
+    adam_body<ZERO_G>(w, g, m, v, n, sc, hp);
+}
+// group forms: z = organization; every organization has its own flat buffers, scalars and step counter
+__global__ void __launch_bounds__(256) sqnorm_stage1_group(const OrgDev* __restrict__ orgs, int b) {
+    const OrgDev& o = orgs[blockIdx.z];
+    sqnorm_stage1_body(o.G, o.n_params, o.partial, BatchRef{o.row_off, o.active, b, 0, 0});
+}
+__global__ void adam_prepare_group(const OrgDev* __restrict__ orgs, int b, int n_partial, AdamHyper hp) {
+    const OrgDev& o = orgs[blockIdx.z];
+    adam_prepare_body(o.partial, n_partial, nullptr, nullptr, o.sc, hp, 0, o.step_dev, o.loss_rows, o.t_batch_cnt + b,
+                      o.loss_buf + b, BatchRef{o.row_off, o.active, b, 0, 0});
+}
+__global__ void __launch_bounds__(256) adam_group(const OrgDev* __restrict__ orgs, AdamHyper hp) {
+    const OrgDev& o = orgs[blockIdx.z];
+    adam_body<true>(o.P, o.G, o.M, o.V, o.n_params, o.sc, hp);
+}
+
+int launch_group_optim(const OrgDev* orgs, int G, int b, int64_t n_params_max, AdamHyper hp, cudaStream_t st) {
+    int nb = kNormBlocks / (G > 4 ? 4 : 1);  // per-organization partial count (fixed -> deterministic)
+    sqnorm_stage1_group<<<dim3(nb, 1, G), 256, 0, st>>>(orgs, b);
+    DMT_LAUNCH_CHECK();
+    adam_prepare_group<<<dim3(1, 1, G), 512, 0, st>>>(orgs, b, nb, hp);
+    DMT_LAUNCH_CHECK();
+    int64_t blocks = (n_params_max / 4 + 255) / 256;
+    int64_t cap = (int64_t)kNumSMs * 16 / G;
+    if (cap < 8) cap = 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adam_group<<<dim3((int)blocks, 1, G), 256, 0, st>>>(orgs, hp);
+    DMT_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_sqnorm_stage1(const float* g, int64_t n, float* partial, BatchRef br, cudaStream_t st) {

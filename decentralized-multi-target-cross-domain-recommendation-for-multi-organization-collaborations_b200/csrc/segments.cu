@@ -169,7 +169,7 @@ int launch_segment_reduce_rows(const int32_t* perm, const int32_t* seg_key, cons
 // multi-chunk segments (popular columns: up to one entry per batch row) write partial rows that a second small
 // kernel adds in chunk order -> still deterministic, and the critical path is one chunk, not the longest segment.
 template <int VEC>
-__global__ void __launch_bounds__(256) segment_chunks_kernel(ChunkedSegs cs, const float* __restrict__ coef,
+__device__ __forceinline__ void segment_chunks_body(ChunkedSegs cs, const float* __restrict__ coef,
                                                              const float* __restrict__ src, float* __restrict__ grad,
                                                              float* __restrict__ bias_grad,
                                                              const int32_t* __restrict__ active) {
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) segment_chunks_kernel(ChunkedSegs cs, con
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256) segment_finish_kernel(ChunkedSegs cs, float* __restrict__ grad,
+__device__ __forceinline__ void segment_finish_body(ChunkedSegs cs, float* __restrict__ grad,
                                                              float* __restrict__ bias_grad,
                                                              const int32_t* __restrict__ active) {
     constexpr int W = VEC * 128;
@@ -284,6 +284,54 @@ __global__ void __launch_bounds__(256) segment_finish_kernel(ChunkedSegs cs, flo
         for (int v = 0; v < VEC; ++v) st4(grad + (int64_t)row_out * W + v * 128 + lane * 4, acc[v]);
         if (bias_grad != nullptr && lane == 0) bias_grad[row_out] = bsum;
     }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_chunks_kernel(ChunkedSegs cs, const float* coef, const float* src,
+                                                             float* grad, float* bias_grad, const int32_t* active) {
+    segment_chunks_body<VEC>(cs, coef, src, grad, bias_grad, active);
+}
+template <int VEC>
+__global__ void __launch_bounds__(256) segment_finish_kernel(ChunkedSegs cs, float* grad, float* bias_grad,
+                                                             const int32_t* active) {
+    segment_finish_body<VEC>(cs, grad, bias_grad, active);
+}
+// side 0: dW4/db4 from (gbuf, A3); side 1: dW1t from (data values, dZ1)
+template <int VEC, bool FINISH>
+__global__ void __launch_bounds__(256) segment_group(const OrgDev* __restrict__ orgs, int b, int side) {
+    const OrgDev& o = orgs[blockIdx.z];
+    ChunkedSegs cs = side == 0 ? o.seg_t : o.seg_d;
+    cs.b = b;
+    const float* coef = side == 0 ? o.gbuf : o.dval_ord;
+    const float* src = side == 0 ? o.a3 : o.dz1;
+    float* grad = o.G + (side == 0 ? o.oW4 : o.oW1);
+    float* bias = side == 0 ? o.G + o.ob4 : nullptr;
+    if (FINISH) segment_finish_body<VEC>(cs, grad, bias, o.active);
+    else segment_chunks_body<VEC>(cs, coef, src, grad, bias, o.active);
+}
+
+int launch_group_segments(const OrgDev* orgs, int G, int b, int side, int n_cols_max, int H1, cudaStream_t st) {
+    int per_org = (kNumSMs * 8 + G - 1) / G;
+    int want = (n_cols_max * 2 + 7) / 8;
+    if (per_org > want) per_org = want;
+    if (per_org < 4) per_org = 4;
+    int fin = (n_cols_max + 7) / 8;
+    if (fin > per_org) fin = per_org;
+    if (fin < 1) fin = 1;
+#define DMT_SEGG(V)                                                                        \
+    do {                                                                                   \
+        segment_group<V, false><<<dim3(per_org, 1, G), 256, 0, st>>>(orgs, b, side);       \
+        DMT_LAUNCH_CHECK();                                                                \
+        segment_group<V, true><<<dim3(fin, 1, G), 256, 0, st>>>(orgs, b, side);            \
+        DMT_LAUNCH_CHECK();                                                                \
+    } while (0)
+    if (H1 == 128) DMT_SEGG(1);
+    else if (H1 == 256) DMT_SEGG(2);
+    else if (H1 == 384) DMT_SEGG(3);
+    else if (H1 == 512) DMT_SEGG(4);
+    else { set_error("segment width must be 128, 256, 384 or 512"); return DMT_E_ARG; }
+#undef DMT_SEGG
+    return 0;
 }
 
 int launch_segment_chunks(ChunkedSegs cs, int n_chunk_max, int n_seg_max, const float* coef, const float* src,

@@ -168,14 +168,14 @@ class FastEpochLayout:
 class OrgEngine:
     """One organization's AAE on the device (Organization.train / predict, reference src/organization.py:140-217)."""
 
-    def __init__(self, data: DeviceCSR, target: DeviceCSR, batch_rows, H1=256, H2=128, loss_kind=0):
+    def __init__(self, data: DeviceCSR, target: DeviceCSR, batch_rows, H1=256, H2=128, loss_kind=0, plan_epochs=1):
         self.data, self.target = data, target
         self.n_rows, self.n_enc = data.shape
         self.n_dec = target.shape[1]
         self.H1, self.H2 = H1, H2
         self.batch_rows = batch_rows
         self.h = native.Org(self.n_rows, self.n_enc, self.n_dec, H1, H2, data.triple(), target.pair(), batch_rows,
-                            loss_kind)
+                            loss_kind, plan_epochs=plan_epochs)
         self.d_len, self.t_len = data.row_len, target.row_len
         self.device = data.indptr.device
         self._keep_alive = []

@@ -76,7 +76,14 @@ def _declare(lib):
         "dmt_dense_bwd_w": (I, [P, P, P, P, I, I, I, P]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
         "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, I, P]),
-        "dmt_org_create": (I, [C.POINTER(P), I, I, I, I, I, P, P, P, L, P, P, L, I, I, P]),
+        "dmt_org_create": (I, [C.POINTER(P), I, I, I, I, I, P, P, P, L, P, P, L, I, I, I, P]),
+        "dmt_group_create": (I, [C.POINTER(P), C.POINTER(P), I, P]),
+        "dmt_group_destroy": (I, [P]),
+        "dmt_group_train": (I, [P, C.POINTER(P), C.POINTER(P), I, I, C.POINTER(L), C.POINTER(L), C.POINTER(C.c_uint64),
+                                D, D, D, D, D, F, C.POINTER(P)]),
+        "dmt_group_sync": (I, [P]),
+        "dmt_group_stream": (P, [P]),
+        "dmt_group_wait_stream": (I, [P, P]),
         "dmt_org_destroy": (I, [P]),
         "dmt_org_num_params": (L, [P]),
         "dmt_org_set_params": (I, [P, P]),
@@ -360,10 +367,53 @@ def ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, loss_kind, nnz, tr
     return pred, gout, dz3, loss_rows, n_t
 
 
+class Group:
+    """Handle of an organization group (dmt_group_*): lockstep training of several organizations, one launch per
+    step kernel for all of them."""
+
+    def __init__(self, orgs):
+        lib = load()
+        self._lib = lib
+        self.orgs = list(orgs)
+        arr = (C.c_void_p * len(self.orgs))(*[o.h for o in self.orgs])
+        self.h = C.c_void_p()
+        check(lib.dmt_group_create(C.byref(self.h), arr, len(self.orgs), None), "dmt_group_create")
+
+    def train(self, rows, row_off, n_rows_total, n_batches, n_t, n_d, seeds, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+              weight_decay=5e-4, max_norm=1.0, batch_loss=None):
+        n = len(self.orgs)
+        P = C.c_void_p
+        rows_a = (P * n)(*[ptr(r) for r in rows])
+        off_a = (P * n)(*[ptr(r) for r in row_off])
+        nt_a = (C.c_int64 * n)(*[int(x) for x in n_t])
+        nd_a = (C.c_int64 * n)(*[int(x) for x in n_d])
+        seed_a = (C.c_uint64 * n)(*[int(x) for x in seeds])
+        loss_a = (P * n)(*[ptr(t) for t in batch_loss]) if batch_loss is not None else None
+        check(self._lib.dmt_group_wait_stream(self.h, stream()), "dmt_group_wait_stream")
+        check(self._lib.dmt_group_train(self.h, rows_a, off_a, int(n_rows_total), int(n_batches), nt_a, nd_a, seed_a,
+                                        float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                        float(max_norm), loss_a), "dmt_group_train")
+
+    def sync(self):
+        check(self._lib.dmt_group_sync(self.h), "dmt_group_sync")
+
+    def close(self):
+        if self.h:
+            self._lib.dmt_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Org:
     """Handle of the device-resident organization engine (dmt_org_*)."""
 
-    def __init__(self, n_rows, n_enc, n_dec, H1, H2, d_csr, t_csr, batch_rows, loss_kind, own_stream=True):
+    def __init__(self, n_rows, n_enc, n_dec, H1, H2, d_csr, t_csr, batch_rows, loss_kind, own_stream=True,
+                 plan_epochs=1):
         lib = load()
         self._lib = lib
         self.d_csr = d_csr  # (indptr, indices, val) int32/int32/float32 CUDA tensors, kept alive here
@@ -372,7 +422,7 @@ class Org:
         st = None if own_stream else stream()
         check(lib.dmt_org_create(C.byref(self.h), n_rows, n_enc, n_dec, H1, H2, ptr(d_csr[0]), ptr(d_csr[1]),
                                  ptr(d_csr[2]), d_csr[1].numel(), ptr(t_csr[0]), ptr(t_csr[1]), t_csr[1].numel(),
-                                 batch_rows, loss_kind, st), "dmt_org_create")
+                                 batch_rows, loss_kind, int(plan_epochs), st), "dmt_org_create")
         self.n_params = lib.dmt_org_num_params(self.h)
         self.H2 = H2
         self._target = None

@@ -186,10 +186,13 @@ typedef struct dmt_org dmt_org_t;
  * data CSR: n_rows x n_enc (the organization's own columns, local ids); target CSR: n_rows x n_dec (ALL columns;
  * values = residuals, set every round with dmt_org_set_target). The CSR arrays are borrowed device pointers that
  * must outlive the handle; hidden sizes are the reference's [H1=256, H2=128] (src/utils.py:166-171).
- * stream NULL: the handle creates a private non-blocking stream (organizations then run concurrently). */
+ * stream NULL: the handle creates a private non-blocking stream (organizations then run concurrently).
+ * plan_epochs >= 1: how many local epochs one plan / one graph may cover (sizes the plan buffers: ~40 B per target
+ * entry and planned epoch — 180 GB of HBM buy whole-round plans at ML1M/Douban/Amazon shape). */
 int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, int H2, const int32_t* d_indptr,
                    const int32_t* d_indices, const float* d_val, int64_t d_nnz, const int32_t* t_indptr,
-                   const int32_t* t_indices, int64_t t_nnz, int batch_rows, int loss_kind, void* stream);
+                   const int32_t* t_indices, int64_t t_nnz, int batch_rows, int loss_kind, int plan_epochs,
+                   void* stream);
 int dmt_org_destroy(dmt_org_t* org);
 /* number of fp32 parameters; flat layout: W1t[n_enc*H1] b1[H1] W2[H2*H1] b2[H2] W3[H1*H2] b3[H1] W4[n_dec*H1] b4[n_dec] */
 int64_t dmt_org_num_params(const dmt_org_t* org);
@@ -220,6 +223,31 @@ void* dmt_org_stream(dmt_org_t* org);
  * `stream`; signal = `stream` waits for work already enqueued on the handle's stream. */
 int dmt_org_wait_stream(dmt_org_t* org, void* stream);
 int dmt_org_signal_stream(dmt_org_t* org, void* stream);
+
+/* ------------------------------------------------------------------ organization groups */
+
+typedef struct dmt_group dmt_group_t;
+
+/* A group trains several organizations of one rank in lockstep: every step kernel is launched ONCE with the
+ * organization as grid dimension z (same rows, hidden sizes, batch size and target width required). This is the
+ * same arithmetic as dmt_org_train_epoch per organization — organizations never share data — but ~20 launches per
+ * step for all of them instead of ~20 per organization (the reference loops organizations in Python,
+ * src/train_recsys_assist.py:148-149). */
+int dmt_group_create(dmt_group_t** out, dmt_org_t* const* orgs, int n, void* stream);
+int dmt_group_destroy(dmt_group_t* g);
+/* All local epochs of one round for every organization of the group: organization i trains on batches
+ * rows[i][row_off[i][b] .. row_off[i][b+1]) for b < n_batches (n_batches = epochs x batches per epoch; the layout
+ * rules of dmt_org_train_epoch apply; device pointers in host arrays of length n). Dropout comes from the on-device
+ * generator seeded with seeds[i]. batch_loss[i] (device, may be NULL) receives every batch's mean loss.
+ * Call dmt_org_set_params / dmt_org_set_target on the members first; afterwards their streams are ordered after
+ * the group's work (dmt_org_predict / dmt_org_get_params see the trained parameters). */
+int dmt_group_train(dmt_group_t* g, const int32_t* const* rows, const int32_t* const* row_off, int n_rows_total,
+                    int n_batches, const int64_t* n_t_entries, const int64_t* n_d_entries, const uint64_t* seeds,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, float max_norm,
+                    float* const* batch_loss);
+int dmt_group_sync(dmt_group_t* g);
+void* dmt_group_stream(dmt_group_t* g);
+int dmt_group_wait_stream(dmt_group_t* g, void* stream);
 
 /* ------------------------------------------------------------------ measurement support (bench.py) */
 

@@ -55,3 +55,42 @@ def test_two_emulated_ranks_match_one():
             assert torch.isfinite(one.F[k]).all()
     for r in [one] + ranks:
         r.close()
+
+
+def test_group_lockstep_matches_per_organization_graphs():
+    """dmt_group_train (one launch per step kernel for all organizations) against the per-organization epoch graphs:
+    same seeds -> same parameters and predictions up to the summation order of the gradient norm."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import roundloop, runner, synth
+    from dmtcdr_b200.config import make_cfg
+
+    control = "Douban_user_explicit_ae_0_genre_assist_constant-0.3_constant"
+    make_cfg(control, device="cuda", seed=0)
+    data = synth.make_rating_data("tiny-Douban", seed=0)
+    torch.manual_seed(0)
+    dataset = runner.fetch_dataset(data)
+    runner.process_dataset(dataset)
+    split = [s.numpy() for s in runner.split_dataset(dataset)]
+    mats = {k: (dataset[k].data, dataset[k].target) for k in dataset}
+    kw = dict(target_mode="explicit", batch_rows=40, clamp=True, ar=0.3, local_epochs=3, device="cuda:0", seed=5)
+    a = roundloop.AssistRounds(mats, split, group=False, **kw)
+    b = roundloop.AssistRounds(mats, split, group=True, **kw)
+    assert b.group is not None
+    for r in (a, b):
+        r.round0()
+    for t in (1, 2):
+        a.run_round(t)
+        b.run_round(t)
+        a.sync()
+        b.sync()
+        for org in a.my_orgs:
+            la, lb = a.round_losses[t][org].cpu(), b.round_losses[t][org].cpu()
+            assert float((la - lb).abs().max()) <= 1e-5 * float(la.abs().max())
+            pa, pb = a.eng[org].params().cpu(), b.eng[org].params().cpu()
+            assert float((pa - pb).abs().max()) <= 5e-4 * float(pa.abs().max())
+        for k in ("train", "test"):
+            assert float((a.F[k] - b.F[k]).abs().max()) <= 1e-4 * float(a.F[k].abs().max())
+    a.close()
+    b.close()

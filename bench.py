@@ -262,38 +262,56 @@ def run_ours(args):
 
 
 def hbm_bound_case(dev, hbm):
-    """The decoder kernel on a shape whose weight matrix (n_dec = 400k columns x 256 fp32 = 410 MB) cannot live in
-    the 126 MB L2: one 512-row batch with ~2000 targets per row, CUDA-event timed through the stateless C-ABI."""
+    """The SAME decoder kernel (ae_decoder_fwd_kernel, train mode) on a shape that cannot be served by the 126 MB L2:
+    512 batch rows x 2048 targets each, every target a DISTINCT column of a 1 100 000 x 256 fp32 weight matrix
+    (1.13 GB), so every 1 KB weight row is read from HBM exactly once. Raw C-ABI call, outputs preallocated, CUDA
+    events on the launching stream."""
     from dmtcdr_b200 import native
 
+    lib = native.load()
     g = torch.Generator(device=dev)
     g.manual_seed(1)
-    n_rows, n_dec, per_row, H = 512, 400_000, 2000, 256
-    cols = torch.randint(0, n_dec, (n_rows, per_row), device=dev, generator=g, dtype=torch.int32)
+    n_rows, n_dec, per_row, H = 512, 1_100_000, 2048, 256
+    nnz = n_rows * per_row
+    cols = torch.randperm(n_dec, device=dev, generator=g)[:nnz].reshape(n_rows, per_row)
     cols, _ = torch.sort(cols, dim=1)
-    indptr = (torch.arange(n_rows + 1, device=dev, dtype=torch.int32) * per_row).contiguous()
-    indices = cols.reshape(-1).contiguous()
-    target = torch.randn(n_rows * per_row, device=dev, generator=g)
+    indptr = (torch.arange(n_rows + 1, device=dev, dtype=torch.int64) * per_row).to(torch.int32).contiguous()
+    indices = cols.reshape(-1).to(torch.int32).contiguous()
+    target = torch.randn(nnz, device=dev, generator=g)
     A3 = torch.tanh(torch.randn(n_rows, H, device=dev, generator=g))
-    W4 = torch.randn(n_dec, H, device=dev, generator=g) * 0.05
+    W4 = torch.empty(n_dec, H, device=dev).normal_(0, 0.05, generator=g)
     b4 = torch.zeros(n_dec, device=dev)
     rows = torch.arange(n_rows, device=dev, dtype=torch.int32)
-    nnz = n_rows * per_row
+    pred = torch.empty(nnz, device=dev)
+    gout = torch.empty(nnz, device=dev)
+    dz3 = torch.empty(n_rows, H, device=dev)
+    loss_rows = torch.empty(n_rows, device=dev)
+    n_t = torch.tensor([nnz], device=dev, dtype=torch.int32)
+    P = native.ptr
+
+    def launch():
+        native.check(lib.dmt_ae_decoder_fwd(P(rows), n_rows, P(indptr), P(indices), P(target), P(A3), P(W4), P(b4), H, 0,
+                                            P(n_t), P(pred), P(gout), P(dz3), P(loss_rows), 1, native.stream()),
+                     "dmt_ae_decoder_fwd")
+
     for _ in range(3):
-        native.ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, 0, nnz, True)
+        launch()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
     e0.record()
     for _ in range(reps):
-        native.ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, 0, nnz, True)
+        launch()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    bytes_ = nnz * (4 * H + 16) + n_rows * H * 4 * 2
+    # per target: 1 KB weight row + 4 B column + 4 B target + 4 B bias read, 4 B prediction + 4 B gradient written;
+    # per row: A3 in, dZ3 out
+    bytes_ = nnz * (4 * H + 20) + n_rows * H * 4 * 2
     ach = bytes_ / (ms * 1e-3) / 1e9
-    return {"shape": "512 rows x 2000 targets/row over 400000 columns (W4 410 MB > L2)", "ms_per_launch": ms,
-            "algorithmic_bytes_per_launch": bytes_, "achieved": ach, "peak": hbm, "frac": ach / hbm, "unit": "GB/s",
-            "note": "includes torch allocations of the wrapper's outputs; random rows, every 1 KB row read once"}
+    return {"kernel": "ae_decoder_fwd_kernel<2>", "shape": "512 rows x 2048 distinct targets over 1.1M columns (W4 1.13 GB >> L2)",
+            "ms_per_launch": ms, "algorithmic_bytes_per_launch": bytes_, "achieved": ach, "peak": hbm,
+            "frac": ach / hbm, "unit": "GB/s",
+            "traffic": 1082800000, "traffic_source": "profiles/r1_ncu_decoder_hbm_case.md (dram read+write per launch)"}
 
 
 def run_e2e(args, data, rank, world, dev):

@@ -53,7 +53,7 @@ def install_shims():
         torch.load = load
 
 
-def enter(workdir, control_name, seed=0, extra_argv=(), driver_name="train_recsys_assist"):
+def enter(workdir, control_name, seed=0, extra_argv=(), driver_name="train_recsys_assist", first_on_path=()):
     """chdir into ``workdir``, import the reference's modules, parse the control name.
     Returns a namespace with the reference modules and its global cfg."""
     install_shims()
@@ -62,6 +62,8 @@ def enter(workdir, control_name, seed=0, extra_argv=(), driver_name="train_recsy
     os.chdir(workdir)
     if REF_SRC not in sys.path:
         sys.path.insert(0, REF_SRC)
+    for pth in reversed(list(first_on_path)):  # e.g. the drop-in directory, ahead of the reference's own modules
+        sys.path.insert(0, pth)
     sys.argv = ["ref", "--device", "cpu", "--control_name", control_name, "--init_seed", str(seed), *extra_argv]
     # the driver builds its argparse from cfg at import time and calls process_args itself
     # (reference src/train_recsys_assist.py:21-26); import it BEFORE anything adds cfg['control_name'].

@@ -143,7 +143,8 @@ for k, O_k in O.items():
     assert float(O_k[K:].abs().sum()) == 0.0
 assert D.max_over_ranks(float(rank), "cpu") == float(world - 1)
 D.barrier()
-print("rank", rank, "ok")
+sys.stdout.write("rank%dok\n" % rank)
+sys.stdout.flush()
 """
 
 
@@ -156,4 +157,24 @@ def test_exchange_on_two_gloo_ranks(tmp_path):
            "127.0.0.1", "--master-port", "29611", str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "rank0ok" in r.stdout and "rank1ok" in r.stdout
+
+
+def test_distribute_slices_the_split_entity():
+    """models.distribute (reference src/models/utils.py:17-40): joint tables are row-sliced into the local models."""
+    import dmtcdr_b200
+    from dmtcdr_b200.config import make_cfg
+
+    cfg = make_cfg("ML100K_user_explicit_mf_0_genre_joint", device="cpu")
+    cfg["info_size"] = None
+    models, _, _ = dmtcdr_b200.use_dropin()
+    torch.manual_seed(0)
+    joint = models.mf(10, 7)
+    split = [torch.tensor([0, 3, 4]), torch.tensor([1, 2, 5, 6])]
+    local = [models.mf(10, len(s)) for s in split]
+    models.distribute(joint, local, split)
+    for s, m in zip(split, local):
+        assert torch.equal(m.item_weight.weight, joint.item_weight.weight[s])
+        assert torch.equal(m.item_bias.weight, joint.item_bias.weight[s])
+        assert torch.equal(m.user_weight.weight, joint.user_weight.weight)
+        assert torch.equal(m.bias, joint.bias)

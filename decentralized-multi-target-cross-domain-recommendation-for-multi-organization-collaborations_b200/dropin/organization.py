@@ -210,8 +210,15 @@ class Organization:
         if rng == 'reference':
             np.random.seed(cfg['seed'])  # side effect of make_data_loader (src/data.py:76)
         num_users, num_items = dataset.num_users, dataset.num_items
-        model = models.ae(num_users['data'], num_items['data'], num_users['target'], num_items['target'])
-        flat0 = E.flat_from_state_dict(model.state_dict(), dev)
+        if rng == 'reference':
+            # parameters created exactly like the reference does (same modules, same draws from torch's CPU generator)
+            model = models.ae(num_users['data'], num_items['data'], num_users['target'], num_items['target'])
+            flat0 = E.flat_from_state_dict(model.state_dict(), dev)
+        else:
+            # same initial distribution (xavier-uniform weights, zero biases, src/models/ae.py:22-28,89-96) drawn by the
+            # device generator straight into the engine's layout: no host init, no upload
+            from dmtcdr_b200 import roundloop
+            flat0 = roundloop.init_flat_params(eng.n_enc, eng.n_dec, eng.H1, eng.H2, dev)
         res = getattr(dataset.target, '_dmt_residual_dev', None)
         if res is None:
             res = E.to_dev(np.asarray(dataset.target.data, dtype=np.float32), dev)
@@ -236,7 +243,7 @@ class Organization:
             loss_all = torch.cat(losses)
         else:
             for _ in range(n_epochs):
-                layouts.append(E.EpochLayout(E.fast_perm_batches(d.shape[0], bs), eng.d_len, eng.t_len))
+                layouts.append(E.FastEpochLayout(torch.randperm(d.shape[0]).numpy(), bs, eng.d_len, eng.t_len))
             loss_all = torch.zeros(sum(len(l.active) for l in layouts), device=dev)
             seeds = [E.he_seed(cfg['seed'], self.organization_id, iter, e) for e in range(n_epochs)]
             eng.enqueue_epochs(layouts, seeds, hp=hp, loss_out=loss_all)

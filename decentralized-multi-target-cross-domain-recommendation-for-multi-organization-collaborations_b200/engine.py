@@ -32,8 +32,14 @@ def to_dev(x, device):
 
 
 def to_host(t):
+    """Device -> host through pinned staging memory (torch caches the pinned blocks), counted in XFER."""
     XFER["d2h"] += t.numel() * t.element_size()
-    return t.cpu()
+    if not t.is_cuda or t.numel() < (1 << 14):
+        return t.cpu()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out
 
 
 class DeviceCSR:

@@ -97,6 +97,23 @@ def make_split_dataset(dataset, data_split):
     return out
 
 
+def pair_batch(ds, rows):
+    """COO batch of the listed rows in the reference's PairInput format (src/data.py:84-137): the aligned id repeated
+    per entry, concatenated in the given row order; train keys and target_* keys."""
+    mode = cfg['data_mode']
+    other = 'item' if mode == 'user' else 'user'
+    rows = np.asarray(rows, dtype=np.int64)
+    out = {}
+    for pre, m in (('', ds.data), ('target_', ds.target)):
+        starts, ends = m.indptr[rows], m.indptr[rows + 1]
+        cnt = (ends - starts).astype(np.int64)
+        pos = np.repeat(starts.astype(np.int64) - np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt) + np.arange(cnt.sum())
+        out[pre + mode] = torch.from_numpy(np.repeat(rows, cnt))
+        out[pre + other] = torch.from_numpy(m.indices[pos].astype(np.int64))
+        out[pre + 'rating'] = torch.from_numpy(m.data[pos].astype(np.float32))
+    return out
+
+
 def initialize(dataset, assist, organization, metric, logger):
     """Round 0: every organization's base predictor, assembled into the global output / target matrices
     (src/train_recsys_assist.py:98-141)."""

@@ -163,8 +163,11 @@ def run_reference_arm(args):
 def run_ours(args):
     from dmtcdr_b200 import dist as D
 
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would break the one-JSON-line contract
+    # Libraries (NCCL's version banner, ...) print to the C-level stdout; the contract is ONE JSON line there. Everything
+    # before the final print is redirected to stderr at the file-descriptor level.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = D.init_from_env()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -260,6 +263,8 @@ def run_ours(args):
                                     "2 x 72 MB prediction matrices, plans) exceeds 126 MB"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
             "cpu_baseline": cpu, "mf_joint": mf}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
 
 

@@ -128,6 +128,31 @@ def make_rating_data(name: str = "ML1M", seed: int = 0, shape=None, min_per_user
     return RatingData(name, train, test, item_attr, user_profile)
 
 
+def make_scaled_data(M, N, nnz, n_genre=8, seed=0, name="scaled"):
+    """Large synthetic shapes (config 5 family: up to 1M x 500K): Zipf-like item draws by inverse CDF, duplicates
+    dropped, so generation is O(nnz log N) instead of the O(M*N) Gumbel top-k used for the small shapes."""
+    rng = np.random.default_rng(seed)
+    pop = 1.0 / np.arange(1, N + 1) ** 0.8
+    cdf = np.cumsum(pop[rng.permutation(N)])
+    cdf /= cdf[-1]
+    per = max(1, int(nnz * 1.08 / M))
+    rows = np.repeat(np.arange(M, dtype=np.int64), per)
+    cols = np.searchsorted(cdf, rng.random(rows.size)).astype(np.int64)
+    key = np.unique(rows * N + cols)
+    if key.size > nnz:
+        key = np.sort(rng.choice(key, size=nnz, replace=False))
+    rows, cols = key // N, key % N
+    rating = rng.choice(np.arange(1, 6), size=key.size, p=_RATING_P).astype(np.float32)
+    idx = rng.permutation(key.size)
+    n_train = int(key.size * 0.9)
+    tr, te = idx[:n_train], idx[n_train:]
+    train = csr_matrix((rating[tr], (rows[tr], cols[tr])), shape=(M, N))
+    test = csr_matrix((rating[te], (rows[te], cols[te])), shape=(M, N))
+    item_attr = np.zeros((N, n_genre), dtype=np.float32)
+    item_attr[np.arange(N), rng.integers(0, n_genre, size=N)] = 1
+    return RatingData(name, train, test, item_attr, None)
+
+
 def _profile_blocks(P):
     if P == 30:
         return [7, 2, 21]  # age, gender, occupation (reference src/datasets/movielens.py:409-415)

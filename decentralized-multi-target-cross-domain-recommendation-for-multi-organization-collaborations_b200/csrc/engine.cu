@@ -72,6 +72,9 @@ struct dmt_org {
     int32_t *t_nch_row, *t_chunk_off, *t_chunk_row, *t_batch_chunk;
     float *dz_part, *loss_part;
     int64_t dec_chunk_cap, dec_part_rows;
+    // tensor-core decoder (decoder_tc.cu)
+    int dec_mode, dec_passes;
+    float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
     void* sort_temp;
     int64_t sort_temp_bytes;
     // epoch inputs (stable addresses for the graph)
@@ -341,7 +344,21 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
     }
     // (no gradient zeroing pass: Adam clears every gradient it consumes, dmt_org_set_params clears the first)
     // decoder + loss + dZ3
-    if (WANT(K_DEC)) {
+    const bool tc = o->dec_mode == 1;
+    float* tc_loss_part = tc ? o->tc_scratch + (int64_t)decoder_tc_splits(
+                                   o->n_dec, decoder_tc_chunks_per_split(B, o->n_dec, H1)) * B * H1
+                             : nullptr;
+    if (WANT(K_DEC) && tc) {
+        if ((rc = launch_decoder_tc_fwd(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1, o->n_dec,
+                                        DMT_LOSS_MSE, o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, tc_loss_part,
+                                        o->dec_passes, B, br, st)))
+            return rc;
+        if ((rc = launch_decoder_tc_bwd_a(o->rows_buf, o->t_indptr, o->t_indices, o->gbuf, o->pt.ent_off, o->a3, W4,
+                                          H1, o->n_dec, o->tc_scratch, tc_loss_part, o->dz3, o->loss_rows, 1,
+                                          o->dec_passes, B, br, st)))
+            return rc;
+    }
+    if (WANT(K_DEC) && !tc) {
         DecChunks dc{o->t_chunk_off, o->t_chunk_row, o->t_batch_chunk, o->dz_part, o->loss_part};
         if ((rc = launch_ae_decoder_chunks(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1,
                                            DMT_LOSS_MSE, o->pt.batch_cnt, o->pt.ent_off, dc, o->gbuf, o->dz3,
@@ -349,7 +366,12 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
             return rc;
     }
     // dW4, db4: segmented over (batch, target column)
-    if (WANT(K_SEG_W4)) {
+    if (WANT(K_SEG_W4) && tc) {
+        if ((rc = launch_decoder_tc_bwd_w(o->rows_buf, o->t_indptr, o->t_indices, o->gbuf, o->pt.ent_off, o->a3, H1,
+                                          o->n_dec, G + o->oW4, G + o->ob4, o->dec_passes, B, br, st)))
+            return rc;
+    }
+    if (WANT(K_SEG_W4) && !tc) {
         ChunkedSegs cs{o->pt.perm, o->pt.ent_row, o->pt.seg_key, o->pt.seg_off, o->pt.batch_seg_off,
                        o->pt.seg_chunk_off, o->pt.chunk_seg, o->pt.batch_chunk_off, o->pt.part, o->pt.part_bias, b,
                        o->n_dec};
@@ -400,7 +422,7 @@ static int free_all(dmt_org* o) {
     free_side(o->pt); free_side(o->pd);
     cudaFree(o->gbuf); cudaFree(o->dval_ord); cudaFree(o->row_batch); cudaFree(o->active); cudaFree(o->sort_temp);
     cudaFree(o->t_nch_row); cudaFree(o->t_chunk_off); cudaFree(o->t_chunk_row); cudaFree(o->t_batch_chunk);
-    cudaFree(o->dz_part); cudaFree(o->loss_part);
+    cudaFree(o->dz_part); cudaFree(o->loss_part); cudaFree(o->tc_scratch);
     cudaFree(o->rows_buf); cudaFree(o->row_off_buf); cudaFree(o->keep_buf); cudaFree(o->seed_dev);
     cudaFree(o->loss_buf); cudaFree(o->partial); cudaFree(o->sc); cudaFree(o->step_dev);
     if (o->ev) cudaEventDestroy(o->ev);
@@ -479,6 +501,8 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     A(dalloc(&o->t_nch_row, o->rows_cap + 2)); A(dalloc(&o->t_chunk_off, o->rows_cap + 2));
     A(dalloc(&o->t_chunk_row, o->dec_chunk_cap)); A(dalloc(&o->t_batch_chunk, o->nb_cap + 2));
     A(dalloc(&o->dz_part, o->dec_part_rows * H1)); A(dalloc(&o->loss_part, o->dec_part_rows));
+    o->dec_mode = 0; o->dec_passes = 3;
+    A(dalloc(&o->tc_scratch, decoder_tc_scratch_floats(batch_rows, n_dec, H1)));
     A(dalloc(&o->gbuf, t_cap)); A(dalloc(&o->dval_ord, d_cap)); A(dalloc(&o->row_batch, o->rows_cap + 1));
     A(dalloc(&o->active, o->nb_cap + 1));
     o->sort_temp_bytes = sort_segments_temp_bytes(t_cap > d_cap ? t_cap : d_cap);
@@ -512,6 +536,18 @@ int dmt_org_destroy(dmt_org_t* o) {
 }
 
 int64_t dmt_org_num_params(const dmt_org_t* o) { return o ? o->n_params : 0; }
+
+int dmt_org_set_decoder_mode(dmt_org_t* o, int mode, int passes) {
+    DMT_REQUIRE(o && (mode == 0 || mode == 1) && (passes == 1 || passes == 3), "dmt_org_set_decoder_mode: bad argument");
+    if ((o->dec_mode != mode || o->dec_passes != passes) && o->exec) {  // the choice is baked into the captured graph
+        cudaGraphExecDestroy(o->exec);
+        o->exec = nullptr;
+        o->g_nb = -1;
+    }
+    o->dec_mode = mode;
+    o->dec_passes = passes;
+    return 0;
+}
 
 int dmt_org_set_params(dmt_org_t* o, const float* flat) {
     DMT_REQUIRE(o && flat, "dmt_org_set_params: null");
@@ -605,8 +641,15 @@ int dmt_org_predict(dmt_org_t* o, const int32_t* d_indptr, const int32_t* d_indi
             return rc;
         if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, nullptr, nodrop, m, H2, H1, 1, br, st))) return rc;
         if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, m, H1, H2, 1, br, st))) return rc;
-        if ((rc = launch_ae_decoder_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1, o->loss_kind,
-                                        nullptr, nullptr, pred, nullptr, nullptr, nullptr, 0, m, br, st)))
+        if (o->dec_mode == 1) {
+            // rows [lo, hi) of the split: a3 holds them from row 0, the CSR rows are iota_rows[lo + j]
+            if ((rc = launch_decoder_tc_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1, o->n_dec,
+                                            o->loss_kind, nullptr, nullptr, pred, nullptr, nullptr, o->dec_passes, m,
+                                            br, st)))
+                return rc;
+        } else if ((rc = launch_ae_decoder_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1,
+                                               o->loss_kind, nullptr, nullptr, pred, nullptr, nullptr, nullptr, 0, m,
+                                               br, st)))
             return rc;
     }
     return 0;

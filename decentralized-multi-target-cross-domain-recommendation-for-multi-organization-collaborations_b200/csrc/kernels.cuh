@@ -61,6 +61,13 @@ int launch_dense_bwd_x(const float* dY, const float* W, const float* A_prev, Dro
 int launch_dense_bwd_w(const float* dY, const float* X, float* dW, float* db, int m_max, int n, int k, BatchRef br,
                        cudaStream_t st);
 int launch_colsum(const float* dY, int n, float* db, BatchRef br, cudaStream_t st);
+// tcgen05 (UMMA, kind::tf32) variants; passes = 3: 3xTF32 (fp32-level accuracy), 1: single TF32 pass
+int launch_dense_fwd_tc(const float* X, const float* W, const float* b, float* Y, float* Y_pre, Dropout drop, int m_max,
+                        int n, int k, int act, int passes, BatchRef br, cudaStream_t st);
+int launch_dense_bwd_x_tc(const float* dY, const float* W, const float* A_prev, Dropout drop, float* dX, int m_max,
+                          int n, int k, int act_prev, int passes, BatchRef br, cudaStream_t st);
+int launch_dense_bwd_w_tc(const float* dY, const float* X, float* dW, float* db, int m_max, int n, int k, int passes,
+                          BatchRef br, cudaStream_t st);
 
 // ---- ae.cu
 int launch_ae_encoder_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* val,
@@ -72,6 +79,22 @@ int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int3
                           const float* A3, const float* W4, const float* b4, int H, int loss_kind,
                           const int32_t* n_targets, const int32_t* ent_off, float* pred, float* gout, float* dZ3,
                           float* loss_rows, int tanh_deriv, int n_rows_max, BatchRef br, cudaStream_t st);
+
+// ---- decoder_tc.cu: the decoder's last layer as tcgen05 GEMMs with CSR-scattered sparse operands (3xTF32)
+int decoder_tc_chunks_per_split(int n_rows_max, int n_dec, int H);
+int decoder_tc_splits(int n_dec, int chunks_per_split);
+int64_t decoder_tc_scratch_floats(int n_rows_max, int n_dec, int H);  // split-K partials followed by per-tile losses
+int launch_decoder_tc_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
+                          const float* A3, const float* W4, const float* b4, int H, int n_dec, int loss_kind,
+                          const int32_t* n_targets, const int32_t* ent_off, float* pred, float* gout, float* loss_part,
+                          int passes, int n_rows_max, BatchRef br, cudaStream_t st);
+int launch_decoder_tc_bwd_a(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* gbuf,
+                            const int32_t* ent_off, const float* A3, const float* W4, int H, int n_dec, float* part,
+                            const float* loss_part, float* dZ3, float* loss_rows, int tanh_deriv, int passes,
+                            int n_rows_max, BatchRef br, cudaStream_t st);
+int launch_decoder_tc_bwd_w(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* gbuf,
+                            const int32_t* ent_off, const float* A3, int H, int n_dec, float* dW4, float* db4,
+                            int passes, int n_rows_max, BatchRef br, cudaStream_t st);
 
 // ---- segments.cu
 struct SegRef {  // segments [seg_lo, seg_hi) either by value or from device batch_seg_off[b], [b+1]

@@ -13,6 +13,7 @@ Layout (per rank):
 from __future__ import annotations
 
 import math
+import os
 import zlib
 
 import numpy as np
@@ -51,6 +52,9 @@ class DeviceCSR:
             raise ValueError("nnz must fit int32")
         self.shape = m.shape
         self.nnz = int(m.nnz)
+        # ascending column indices inside every row: what the tensor-core decoder's CSR windows need (the storage
+        # order itself is never changed: it is the positional contract of src/assist.py:45-46)
+        self.sorted = bool(m.has_sorted_indices)
         self.indptr_host = np.asarray(m.indptr, dtype=np.int64)
         self.indices_host = np.asarray(m.indices)
         self.indptr = to_dev(self.indptr_host.astype(np.int32), device)
@@ -171,6 +175,14 @@ class FastEpochLayout:
         self.n_d = int(d_len[perm].sum())
 
 
+def decoder_default():
+    """Decoder form of new engines: DMT_DECODER=gather|tc (default tc: tcgen05 GEMMs, 3xTF32)."""
+    mode = os.environ.get("DMT_DECODER", "tc")
+    if mode not in ("tc", "gather"):
+        raise ValueError("Not valid DMT_DECODER: {}".format(mode))
+    return mode
+
+
 class OrgEngine:
     """One organization's AAE on the device (Organization.train / predict, reference src/organization.py:140-217)."""
 
@@ -185,6 +197,15 @@ class OrgEngine:
         self.d_len, self.t_len = data.row_len, target.row_len
         self.device = data.indptr.device
         self._keep_alive = []
+        self.set_decoder(decoder_default() if target.sorted else "gather")
+
+    def set_decoder(self, mode, passes=3):
+        """'tc': decoder last layer as tcgen05 GEMMs (3xTF32 parity mode; passes=1 is reduced precision),
+        'gather': SDDMM + segmented reductions."""
+        if mode == "tc" and not self.target.sorted:
+            raise ValueError("Not valid decoder mode: the tensor-core decoder needs sorted CSR column indices")
+        self.decoder = mode
+        self.h.set_decoder_mode(mode, passes)
 
     def set_round(self, params_flat, residual):
         """Fresh model + optimizer for the round (src/organization.py:144-148) and this round's targets."""
@@ -224,7 +245,12 @@ class OrgEngine:
 
     def predict(self, data: DeviceCSR, target: DeviceCSR, out):
         self.h.wait_current()
-        self.h.predict(data.triple(), target.pair(), target.shape[0], out)
+        if self.decoder == "tc" and not target.sorted:  # this split's CSR cannot take the windowed epilogue
+            self.h.set_decoder_mode("gather")
+            self.h.predict(data.triple(), target.pair(), target.shape[0], out)
+            self.h.set_decoder_mode("tc")
+        else:
+            self.h.predict(data.triple(), target.pair(), target.shape[0], out)
         return out
 
     def sync(self):

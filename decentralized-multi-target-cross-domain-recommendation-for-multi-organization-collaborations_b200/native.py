@@ -74,6 +74,12 @@ def _declare(lib):
         "dmt_dense_fwd": (I, [P, P, P, P, P, P, F, I, I, I, I, P]),
         "dmt_dense_bwd_x": (I, [P, P, P, P, F, P, I, I, I, I, P]),
         "dmt_dense_bwd_w": (I, [P, P, P, P, I, I, I, P]),
+        "dmt_dense_fwd_tc": (I, [P, P, P, P, P, P, F, I, I, I, I, I, P]),
+        "dmt_dense_bwd_x_tc": (I, [P, P, P, P, F, P, I, I, I, I, I, P]),
+        "dmt_dense_bwd_w_tc": (I, [P, P, P, P, I, I, I, I, P]),
+        "dmt_ae_decoder_tc_scratch_floats": (L, [I, I, I]),
+        "dmt_ae_decoder_tc": (I, [P, I, P, P, P, P, P, P, I, I, I, P, I, P, P, P, P, P, P, I, P, P]),
+        "dmt_org_set_decoder_mode": (I, [P, I, I]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
         "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, I, P]),
         "dmt_org_create": (I, [C.POINTER(P), I, I, I, I, I, P, P, P, L, P, P, L, I, I, I, P]),
@@ -339,6 +345,63 @@ def dense_bwd_w(dY, X, want_bias=True):
     return dW, db
 
 
+def dense_fwd_tc(X, W, b, act, keep=None, keep_scale=1.0, passes=3):
+    """tcgen05 form of :func:`dense_fwd` (3xTF32 when passes == 3)."""
+    m, k = X.shape
+    n = W.shape[0]
+    Y = torch.empty(m, n, device=X.device, dtype=torch.float32)
+    Y_pre = torch.empty_like(Y) if keep is not None else None
+    check(load().dmt_dense_fwd_tc(ptr(X), ptr(W), ptr(b), ptr(Y), ptr(Y_pre), ptr(keep), float(keep_scale), m, n, k,
+                                  act, passes, stream()), "dmt_dense_fwd_tc")
+    return Y, Y_pre
+
+
+def dense_bwd_x_tc(dY, W, A_prev, act_prev, keep=None, keep_scale=1.0, passes=3):
+    m, n = dY.shape
+    k = W.shape[1]
+    dX = torch.empty(m, k, device=dY.device, dtype=torch.float32)
+    check(load().dmt_dense_bwd_x_tc(ptr(dY), ptr(W), ptr(A_prev), ptr(keep), float(keep_scale), ptr(dX), m, n, k,
+                                    act_prev, passes, stream()), "dmt_dense_bwd_x_tc")
+    return dX
+
+
+def dense_bwd_w_tc(dY, X, want_bias=True, passes=3):
+    m, n = dY.shape
+    k = X.shape[1]
+    dW = torch.empty(n, k, device=dY.device, dtype=torch.float32)
+    db = torch.empty(n, device=dY.device, dtype=torch.float32) if want_bias else None
+    check(load().dmt_dense_bwd_w_tc(ptr(dY), ptr(X), ptr(dW), ptr(db), m, n, k, passes, stream()),
+          "dmt_dense_bwd_w_tc")
+    return dW, db
+
+
+def ae_decoder_tc(rows, indptr, indices, target, A3, W4, b4, loss_kind, nnz, train, tanh_deriv=True, passes=3):
+    """Tensor-core decoder (dmt_ae_decoder_tc). Returns pred, gout, dZ3, dW4, db4, loss_sum (train) aligned like
+    :func:`ae_decoder_fwd`; the CSR's column indices must ascend inside every row."""
+    lib = load()
+    dev = A3.device
+    H = A3.shape[1]
+    n_dec = W4.shape[0]
+    n_rows = rows.numel()
+    pred = torch.zeros(nnz, device=dev, dtype=torch.float32)
+    gout = dz3 = dW4 = db4 = loss_rows = n_t = scratch = None
+    if train:
+        gout = torch.zeros(nnz, device=dev, dtype=torch.float32)
+        dz3 = torch.empty_like(A3)
+        dW4 = torch.empty_like(W4)
+        db4 = torch.empty(n_dec, device=dev, dtype=torch.float32)
+        loss_rows = torch.empty(max(n_rows, 1), device=dev, dtype=torch.float32)
+        ip = indptr.to(torch.int64)
+        r = rows.to(torch.int64)
+        n_t = (ip[r + 1] - ip[r]).sum().to(torch.int32).reshape(1)
+        scratch = torch.empty(max(1, lib.dmt_ae_decoder_tc_scratch_floats(n_rows, n_dec, H)), device=dev,
+                              dtype=torch.float32)
+    check(lib.dmt_ae_decoder_tc(ptr(rows), n_rows, ptr(indptr), ptr(indices), ptr(target), ptr(A3), ptr(W4), ptr(b4), H,
+                                n_dec, loss_kind, ptr(n_t), passes, ptr(pred), ptr(gout), ptr(dz3), ptr(dW4), ptr(db4),
+                                ptr(loss_rows), int(bool(tanh_deriv)), ptr(scratch), stream()), "dmt_ae_decoder_tc")
+    return pred, gout, dz3, dW4, db4, loss_rows, n_t
+
+
 def ae_encoder_fwd(rows, indptr, indices, val, W1t, b1):
     H = W1t.shape[1]
     A1 = torch.empty(rows.numel(), H, device=W1t.device, dtype=torch.float32)
@@ -426,6 +489,12 @@ class Org:
         self.n_params = lib.dmt_org_num_params(self.h)
         self.H2 = H2
         self._target = None
+
+    def set_decoder_mode(self, mode, passes=3):
+        """mode 'gather' (SDDMM + segmented reductions) or 'tc' (tcgen05 GEMMs; sorted column indices needed)."""
+        code = {"gather": 0, "tc": 1}[mode]
+        check(self._lib.dmt_org_set_decoder_mode(self.h, code, int(passes)), "dmt_org_set_decoder_mode")
+        self.decoder_mode = mode
 
     def set_params(self, flat):
         check(self._lib.dmt_org_set_params(self.h, ptr(flat)), "dmt_org_set_params")

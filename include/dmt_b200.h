@@ -178,6 +178,29 @@ int dmt_ae_decoder_fwd(const int32_t* rows, int n_rows, const int32_t* indptr, c
                        const int32_t* n_targets, float* pred, float* gout, float* dZ3, float* loss_rows, int tanh_deriv,
                        void* stream);
 
+/* Tensor-core forms (tcgen05.mma kind::tf32, accumulators in TMEM; sm_100a only). passes = 3: 3xTF32 — every operand
+ * is split into hi + lo TF32 parts while it is staged into shared memory and three MMAs accumulate per k-step, which
+ * keeps fp32-level accuracy (~2^-21 relative); passes = 1: one TF32 pass (reduced precision, NOT the parity mode).
+ * Same contracts as dmt_dense_fwd / dmt_dense_bwd_x / dmt_dense_bwd_w above (nn.Linear, src/models/ae.py:14-19,44-45). */
+int dmt_dense_fwd_tc(const float* X, const float* W, const float* b, float* Y, float* Y_pre, const uint8_t* keep,
+                     float keep_scale, int m, int n, int k, int act, int passes, void* stream);
+int dmt_dense_bwd_x_tc(const float* dY, const float* W, const float* A_prev, const uint8_t* keep, float keep_scale,
+                       float* dX, int m, int n, int k, int act_prev, int passes, void* stream);
+int dmt_dense_bwd_w_tc(const float* dY, const float* X, float* dW, float* db, int m, int n, int k, int passes,
+                       void* stream);
+
+/* Decoder last layer as dense tensor-core GEMMs with a masked loss epilogue (src/models/ae.py:135-142,153-156 and
+ * its autograd backward): O = A3 W4^T is formed tile by tile in TMEM and only the batch's target entries leave the
+ * SM (pred[e], gout[e] = dloss/do / *n_targets, loss); train mode (gout != NULL) then runs dZ3 = (G W4) [*(1-A3^2)]
+ * and dW4 = G^T A3 [n_dec x H], db4 = column sums of G [n_dec] (db4 may be NULL), with the sparse G scattered from
+ * the CSR into the shared-memory operand tiles. loss_rows[0] = sum of the loss over all entries, loss_rows[1..] = 0.
+ * Column indices must ascend inside every CSR row. H % 128 == 0. scratch >= dmt_ae_decoder_tc_scratch_floats(). */
+int64_t dmt_ae_decoder_tc_scratch_floats(int n_rows, int n_dec, int H);
+int dmt_ae_decoder_tc(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices,
+                      const float* target, const float* A3, const float* W4, const float* b4, int H, int n_dec,
+                      int loss_kind, const int32_t* n_targets, int passes, float* pred, float* gout, float* dZ3,
+                      float* dW4, float* db4, float* loss_rows, int tanh_deriv, float* scratch, void* stream);
+
 /* ------------------------------------------------------------------ device-resident organization engine */
 
 typedef struct dmt_org dmt_org_t;
@@ -194,6 +217,10 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
                    const int32_t* t_indices, int64_t t_nnz, int batch_rows, int loss_kind, int plan_epochs,
                    void* stream);
 int dmt_org_destroy(dmt_org_t* org);
+/* How the decoder's last layer runs in dmt_org_train_epoch / dmt_org_predict: mode 0 = row-gather SDDMM + segmented
+ * reductions (any CSR), mode 1 = tcgen05 GEMMs (dmt_ae_decoder_tc; needs ascending column indices inside every row of
+ * the target CSR and of the CSRs passed to dmt_org_predict). passes: 3 (3xTF32, parity mode) or 1. Default: mode 0. */
+int dmt_org_set_decoder_mode(dmt_org_t* org, int mode, int passes);
 /* number of fp32 parameters; flat layout: W1t[n_enc*H1] b1[H1] W2[H2*H1] b2[H2] W3[H1*H2] b3[H1] W4[n_dec*H1] b4[n_dec] */
 int64_t dmt_org_num_params(const dmt_org_t* org);
 /* Copy parameters in/out (device pointers, flat layout above). set also resets the Adam state: the reference builds

@@ -75,10 +75,11 @@ def unflat_params(flat, n_enc, n_dec, H1=256, H2=128):
     return out
 
 
-@pytest.mark.parametrize("seed,bs", [(0, 50), (1, 64)])
-def test_train_epochs_and_predict(nat, seed, bs):
+@pytest.mark.parametrize("decoder", ["gather", "tc"])
+@pytest.mark.parametrize("seed,bs,n_rows,n_dec", [(0, 50, 130, 100), (1, 64, 130, 100), (2, 150, 400, 300)])
+def test_train_epochs_and_predict(nat, seed, bs, n_rows, n_dec, decoder):
     rng = np.random.default_rng(seed)
-    n_rows, n_enc, n_dec = 130, 30, 100
+    n_enc = 30
     # rows 7,8 have targets but no data; row 9 has nothing; rows 100..129 (a whole batch for bs=50 after sorting the
     # batch list below) have no data -> that batch must be skipped without an optimizer step
     D = rand_csr(rng, n_rows, n_enc, 0.15, empty_rows=(7, 8, 9))
@@ -110,6 +111,7 @@ def test_train_epochs_and_predict(nat, seed, bs):
     d_csr = (cu(D.indptr, torch.int32), cu(D.indices, torch.int32), cu(D.data))
     t_csr = (cu(T.indptr, torch.int32), cu(T.indices, torch.int32))
     org = nat.Org(n_rows, n_enc, n_dec, 256, 128, d_csr, t_csr, bs, 0)
+    org.set_decoder_mode(decoder)  # "tc": the decoder's last layer on tcgen05 (3xTF32), same tolerances
     org.wait_current()
     org.set_params(flat_params(p0).cuda())
     tval = cu(T.data)
@@ -136,8 +138,10 @@ def test_train_epochs_and_predict(nat, seed, bs):
     flat = org.get_params()
     org.sync()
     got_p = unflat_params(flat.cpu(), n_enc, n_dec)
+    # Adam's m/sqrt(v) amplifies rounding of near-zero gradients; 3xTF32 products round ~4x coarser than FFMA fp32
+    tol_p = 5e-4 if decoder == "gather" else 1e-3
     for k, v in ref_p.items():
-        assert rel_err(got_p[k], v) < 5e-4, k
+        assert rel_err(got_p[k], v) < tol_p, k
     # ---- predict (all rows at once) vs the oracle's batched eval forward
     T2 = rand_csr(rng, n_rows, n_dec, 0.1, values="normal")
     ref_pred = train.predict_org_ae(ref_p, D, T2, "user", "explicit", bs)

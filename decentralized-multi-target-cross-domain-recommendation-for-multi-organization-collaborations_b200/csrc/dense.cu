@@ -280,44 +280,53 @@ int launch_group_colsum_dz1(const OrgDev* orgs, int G, int b, int H1, cudaStream
 // C[M x N] = A . B^T on the 5th-generation tensor cores (building blocks and the operand layout: umma.cuh).
 // A(m, k) = A[m * lda + k] when A_KCONTIG else A[k * lda + m]; B(n, k) likewise.
 template <bool A_KCONTIG, bool B_KCONTIG, int DYN, class Epi>
-__global__ void __launch_bounds__(umma::kThreads) umma_gemm_kernel(const float* __restrict__ A, int64_t lda,
-                                                                   const float* __restrict__ B, int64_t ldb, int M,
-                                                                   int N, int K, Epi epi, BatchRef br, int passes) {
+__global__ void __launch_bounds__(umma::kThreads, 1) umma_gemm_kernel(const float* __restrict__ A, int64_t lda,
+                                                                      const float* __restrict__ B, int64_t ldb, int M,
+                                                                      int N, int K, Epi epi, BatchRef br, int passes) {
     extern __shared__ uint8_t umma_smem_raw[];
     int lo_, hi_;
     if (!batch_range(br, lo_, hi_)) return;
     if (DYN == 0) M = hi_ - lo_; else if (DYN == 1) K = hi_ - lo_;
     const int m0 = blockIdx.y * umma::TM, n0 = blockIdx.x * umma::TN;
     if (m0 >= M || n0 >= N) return;  // uniform per CTA, before any allocation or barrier
-    umma::Ctx c = umma::setup(umma_smem_raw, 0);
-    for (int k0 = 0; k0 < K; k0 += umma::TK) {
-        if (A_KCONTIG) umma::stage_kcontig(A, lda, m0, M, k0, K, c.A_hi, c.A_lo, passes);
-        else umma::stage_transposed(A, lda, m0, M, k0, K, c.A_hi, c.A_lo, passes);
-        if (B_KCONTIG) umma::stage_kcontig(B, ldb, n0, N, k0, K, c.B_hi, c.B_lo, passes);
-        else umma::stage_transposed(B, ldb, n0, N, k0, K, c.B_hi, c.B_lo, passes);
-        umma::issue(c, passes);
-        umma::wait(c);
-    }
-    // epilogue: thread t owns accumulator row t (TMEM lane t)
-    const int row = m0 + threadIdx.x;
-#pragma unroll 1
-    for (int c0 = 0; c0 < umma::TN; c0 += 32) {
-        float v[32];
-        if (K > 0) {
-            umma::load_acc32(c, c0, v);  // warp-collective: every lane takes part
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    const umma::Pipe pp = umma::pipe_setup(umma_smem_raw, 0, (K + umma::TK - 1) / umma::TK);
+    const int warp = threadIdx.x >> 5;
+    if (warp < 8) {
+        const int team = warp >> 2, tt = threadIdx.x & (umma::kTeam - 1);
+        const int n_mine = team == 0 ? pp.n0 : pp.n1, first = team == 0 ? 0 : pp.n0;
+        for (int i = 0; i < n_mine; ++i) {
+            const int c = umma::chunk_slot(pp, team, i), k0 = (first + i) * umma::TK;
+            const umma::Stage st = umma::producer_acquire(pp, c);
+            if (A_KCONTIG) umma::stage_kcontig(tt, A, lda, m0, M, k0, K, st.A_hi, st.A_lo, passes);
+            else umma::stage_transposed(tt, A, lda, m0, M, k0, K, st.A_hi, st.A_lo, passes);
+            if (B_KCONTIG) umma::stage_kcontig(tt, B, ldb, n0, N, k0, K, st.B_hi, st.B_lo, passes);
+            else umma::stage_transposed(tt, B, ldb, n0, N, k0, K, st.B_hi, st.B_lo, passes);
+            umma::producer_commit(pp, c);
         }
-        if (row < M) {
+        umma::wait_accumulator(pp);
+        // epilogue: accumulator row = TMEM lane; warps w and w + 4 split the 128 columns
+        const int row = m0 + umma::epi_row(), c0 = umma::epi_col0();
+#pragma unroll 1
+        for (int cc = 0; cc < 64; cc += 32) {
+            float v[32];
+            if (K > 0) {
+                umma::load_acc32(pp, c0 + cc, v);  // warp-collective: every lane takes part
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = n0 + c0 + j;
-                if (col < N) epi(row, col, v[j]);
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + cc + j;
+                    if (col < N) epi(row, col, v[j]);
+                }
             }
         }
+    } else if (warp == umma::kMmaWarp) {
+        umma::mma_loop(pp, passes);
     }
-    umma::teardown(c);
+    umma::pipe_teardown(pp);
 }
 
 template <bool AK, bool BKC, int DYN, class Epi>

@@ -75,6 +75,11 @@ struct dmt_org {
     // tensor-core decoder (decoder_tc.cu)
     int dec_mode, dec_passes;
     float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
+    // tables of per-row CSR windows at 128-column tile borders, one per target CSR seen (train targets, predict splits)
+    struct TabEntry { const int32_t *indptr, *indices; int n_rows; int32_t* tab; };
+    TabEntry tabs[4];
+    int n_tabs;
+    TcTab train_tab;  // table of the training target CSR (set when the tensor-core mode is switched on)
     void* sort_temp;
     int64_t sort_temp_bytes;
     // epoch inputs (stable addresses for the graph)
@@ -348,13 +353,14 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
     float* tc_loss_part = tc ? o->tc_scratch + (int64_t)decoder_tc_splits(
                                    o->n_dec, decoder_tc_chunks_per_split(B, o->n_dec, H1)) * B * H1
                              : nullptr;
+    const TcTab tab = tc ? o->train_tab : TcTab{nullptr, 0};
     if (WANT(K_DEC) && tc) {
         if ((rc = launch_decoder_tc_fwd(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1, o->n_dec,
                                         DMT_LOSS_MSE, o->pt.batch_cnt, o->pt.ent_off, nullptr, o->gbuf, tc_loss_part,
-                                        o->dec_passes, B, br, st)))
+                                        tab, o->dec_passes, B, br, st)))
             return rc;
         if ((rc = launch_decoder_tc_bwd_a(o->rows_buf, o->t_indptr, o->t_indices, o->gbuf, o->pt.ent_off, o->a3, W4,
-                                          H1, o->n_dec, o->tc_scratch, tc_loss_part, o->dz3, o->loss_rows, 1,
+                                          H1, o->n_dec, o->tc_scratch, tc_loss_part, o->dz3, o->loss_rows, 1, tab,
                                           o->dec_passes, B, br, st)))
             return rc;
     }
@@ -368,7 +374,7 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
     // dW4, db4: segmented over (batch, target column)
     if (WANT(K_SEG_W4) && tc) {
         if ((rc = launch_decoder_tc_bwd_w(o->rows_buf, o->t_indptr, o->t_indices, o->gbuf, o->pt.ent_off, o->a3, H1,
-                                          o->n_dec, G + o->oW4, G + o->ob4, o->dec_passes, B, br, st)))
+                                          o->n_dec, G + o->oW4, G + o->ob4, tab, o->dec_passes, B, br, st)))
             return rc;
     }
     if (WANT(K_SEG_W4) && !tc) {
@@ -409,6 +415,27 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
     return 0;
 }
 
+// The table of a CSR (by CSR row id), built on first use on the organization's stream; null when it would be too large
+// (the kernels then binary-search) or when all slots are taken.
+static TcTab tile_tab_for(dmt_org* o, const int32_t* indptr, const int32_t* indices, int n_rows) {
+    for (int i = 0; i < o->n_tabs; ++i)
+        if (o->tabs[i].indptr == indptr && o->tabs[i].indices == indices && o->tabs[i].n_rows == n_rows)
+            return TcTab{o->tabs[i].tab, 2};
+    const int64_t n = decoder_tc_tab_ints(n_rows, o->n_dec);
+    if (o->n_tabs >= 4 || n > (64LL << 20)) return TcTab{nullptr, 0};
+    int32_t* tab = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&tab), (size_t)n * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return TcTab{nullptr, 0};
+    }
+    if (build_tile_tab(nullptr, n_rows, indptr, indices, o->n_dec, tab, o->st)) {
+        cudaFree(tab);
+        return TcTab{nullptr, 0};
+    }
+    o->tabs[o->n_tabs++] = dmt_org::TabEntry{indptr, indices, n_rows, tab};
+    return TcTab{tab, 2};
+}
+
 static bool same_hp(const AdamHyper& a, const AdamHyper& b) {
     return a.lr == b.lr && a.beta1 == b.beta1 && a.beta2 == b.beta2 && a.eps == b.eps &&
            a.weight_decay == b.weight_decay && a.max_norm == b.max_norm;
@@ -423,6 +450,7 @@ static int free_all(dmt_org* o) {
     cudaFree(o->gbuf); cudaFree(o->dval_ord); cudaFree(o->row_batch); cudaFree(o->active); cudaFree(o->sort_temp);
     cudaFree(o->t_nch_row); cudaFree(o->t_chunk_off); cudaFree(o->t_chunk_row); cudaFree(o->t_batch_chunk);
     cudaFree(o->dz_part); cudaFree(o->loss_part); cudaFree(o->tc_scratch);
+    for (int i = 0; i < o->n_tabs; ++i) cudaFree(o->tabs[i].tab);
     cudaFree(o->rows_buf); cudaFree(o->row_off_buf); cudaFree(o->keep_buf); cudaFree(o->seed_dev);
     cudaFree(o->loss_buf); cudaFree(o->partial); cudaFree(o->sc); cudaFree(o->step_dev);
     if (o->ev) cudaEventDestroy(o->ev);
@@ -546,6 +574,7 @@ int dmt_org_set_decoder_mode(dmt_org_t* o, int mode, int passes) {
     }
     o->dec_mode = mode;
     o->dec_passes = passes;
+    if (mode == 1 && o->train_tab.tab == nullptr) o->train_tab = tile_tab_for(o, o->t_indptr, o->t_indices, o->n_rows);
     return 0;
 }
 
@@ -644,8 +673,8 @@ int dmt_org_predict(dmt_org_t* o, const int32_t* d_indptr, const int32_t* d_indi
         if (o->dec_mode == 1) {
             // rows [lo, hi) of the split: a3 holds them from row 0, the CSR rows are iota_rows[lo + j]
             if ((rc = launch_decoder_tc_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1, o->n_dec,
-                                            o->loss_kind, nullptr, nullptr, pred, nullptr, nullptr, o->dec_passes, m,
-                                            br, st)))
+                                            o->loss_kind, nullptr, nullptr, pred, nullptr, nullptr,
+                                            tile_tab_for(o, t_indptr, t_indices, n_rows), o->dec_passes, m, br, st)))
                 return rc;
         } else if ((rc = launch_ae_decoder_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1,
                                                o->loss_kind, nullptr, nullptr, pred, nullptr, nullptr, nullptr, 0, m,

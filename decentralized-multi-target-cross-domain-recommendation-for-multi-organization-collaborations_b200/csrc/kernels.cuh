@@ -81,20 +81,29 @@ int launch_ae_decoder_fwd(const int32_t* rows, const int32_t* indptr, const int3
                           float* loss_rows, int tanh_deriv, int n_rows_max, BatchRef br, cudaStream_t st);
 
 // ---- decoder_tc.cu: the decoder's last layer as tcgen05 GEMMs with CSR-scattered sparse operands (3xTF32)
+// optional table of per-row CSR windows at 128-column tile borders (umma.cuh TileTab): mode 1 = indexed by the batch-row
+// index, 2 = by the CSR row id; tab == null: the kernels binary-search instead
+struct TcTab {
+    const int32_t* tab;
+    int mode;
+};
+int64_t decoder_tc_tab_ints(int64_t n_rows, int n_dec);
+int build_tile_tab(const int32_t* rows, int n_rows, const int32_t* indptr, const int32_t* indices, int n_dec,
+                   int32_t* tab, cudaStream_t st);
 int decoder_tc_chunks_per_split(int n_rows_max, int n_dec, int H);
 int decoder_tc_splits(int n_dec, int chunks_per_split);
 int64_t decoder_tc_scratch_floats(int n_rows_max, int n_dec, int H);  // split-K partials followed by per-tile losses
 int launch_decoder_tc_fwd(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
                           const float* A3, const float* W4, const float* b4, int H, int n_dec, int loss_kind,
                           const int32_t* n_targets, const int32_t* ent_off, float* pred, float* gout, float* loss_part,
-                          int passes, int n_rows_max, BatchRef br, cudaStream_t st);
+                          TcTab tab, int passes, int n_rows_max, BatchRef br, cudaStream_t st);
 int launch_decoder_tc_bwd_a(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* gbuf,
                             const int32_t* ent_off, const float* A3, const float* W4, int H, int n_dec, float* part,
-                            const float* loss_part, float* dZ3, float* loss_rows, int tanh_deriv, int passes,
+                            const float* loss_part, float* dZ3, float* loss_rows, int tanh_deriv, TcTab tab, int passes,
                             int n_rows_max, BatchRef br, cudaStream_t st);
 int launch_decoder_tc_bwd_w(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* gbuf,
                             const int32_t* ent_off, const float* A3, int H, int n_dec, float* dW4, float* db4,
-                            int passes, int n_rows_max, BatchRef br, cudaStream_t st);
+                            TcTab tab, int passes, int n_rows_max, BatchRef br, cudaStream_t st);
 
 // ---- segments.cu
 struct SegRef {  // segments [seg_lo, seg_hi) either by value or from device batch_seg_off[b], [b+1]

@@ -78,6 +78,8 @@ def test_group_lockstep_matches_per_organization_graphs():
     a = roundloop.AssistRounds(mats, split, group=False, **kw)
     b = roundloop.AssistRounds(mats, split, group=True, **kw)
     assert b.group is not None
+    for eng in a.eng.values():  # the group launches use the gather decoder: compare like with like
+        eng.set_decoder("gather")
     for r in (a, b):
         r.round0()
     for t in (1, 2):

@@ -20,6 +20,8 @@
 
 namespace dmt {
 
+constexpr int kForkEvents = 8;
+
 struct PlanSide {  // per-matrix (targets or data) epoch plan buffers
     int64_t cap = 0;                // entry capacity
     int32_t* ent_off = nullptr;     // [rows_cap + 1] offsets of each batch-row in the batch-ordered entry space
@@ -93,6 +95,9 @@ struct dmt_org {
     AdamScalars* sc;
     int* step_dev;
     cudaEvent_t ev;
+    // backward fan-out: auxiliary streams and fork/join events (parallel branches of the captured epoch graph)
+    cudaStream_t aux[3];
+    cudaEvent_t fev[8];
     // graph cache
     cudaGraphExec_t exec;
     long long g_kernels;  // our kernel launches captured in the graph
@@ -371,10 +376,29 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
                                            o->loss_rows, B, br, st)))
             return rc;
     }
-    // dW4, db4: segmented over (batch, target column)
+    // Backward fan-out. Once the decoder has produced g (gbuf) and dZ3 the rest of the backward pass is a DAG, not a
+    // chain: {dW4, db4} | {dW3, db3} | dZ2 -> ({dW2, db2} | dZ1 -> ({dW1} | db1)). The branches are enqueued on the
+    // organization's auxiliary streams between event forks/joins; under stream capture they become parallel branches
+    // of the epoch graph, so a step's critical path is the dZ2 -> dZ1 -> dW1 chain instead of the sum of all kernels.
+    // (`only` >= 0, the per-class profiler, keeps everything on the main stream.)
+    const bool par = only < 0;
+    cudaStream_t sA = par ? o->aux[0] : st, sB = par ? o->aux[1] : st, sC = par ? o->aux[2] : st;
+    int ev_i = 0;
+    auto fork = [&](cudaStream_t from, cudaStream_t to) -> int {  // `to` continues after everything enqueued on `from`
+        if (from == to) return 0;
+        cudaEvent_t ev = o->fev[ev_i++ % kForkEvents];
+        DMT_CUDA(cudaEventRecord(ev, from));
+        DMT_CUDA(cudaStreamWaitEvent(to, ev, 0));
+        return 0;
+    };
+    if (only < 0 || only == K_SEG_W4 || only == K_DENSE_BWD) {
+        if ((rc = fork(st, sA))) return rc;
+        if ((rc = fork(st, sB))) return rc;
+    }
+    // dW4, db4: segmented over (batch, target column) — or the tensor-core G^T A3 — on branch A
     if (WANT(K_SEG_W4) && tc) {
         if ((rc = launch_decoder_tc_bwd_w(o->rows_buf, o->t_indptr, o->t_indices, o->gbuf, o->pt.ent_off, o->a3, H1,
-                                          o->n_dec, G + o->oW4, G + o->ob4, tab, o->dec_passes, B, br, st)))
+                                          o->n_dec, G + o->oW4, G + o->ob4, tab, o->dec_passes, B, br, sA)))
             return rc;
     }
     if (WANT(K_SEG_W4) && !tc) {
@@ -382,26 +406,30 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
                        o->pt.seg_chunk_off, o->pt.chunk_seg, o->pt.batch_chunk_off, o->pt.part, o->pt.part_bias, b,
                        o->n_dec};
         if ((rc = launch_segment_chunks(cs, o->n_dec * 2, o->n_dec, o->gbuf, o->a3, H1, G + o->oW4, G + o->ob4,
-                                        o->active, st)))
+                                        o->active, sA)))
             return rc;
     }
-    // dense backward
+    // dense backward: dW3/db3 on branch B, dZ2 on the main stream, then dW2/db2 on branch C next to dZ1
     if (WANT(K_DENSE_BWD)) {
-        if ((rc = launch_dense_bwd_w(o->dz3, o->c, G + o->oW3, G + o->ob3, B, H1, H2, br, st))) return rc;
+        if ((rc = launch_dense_bwd_w(o->dz3, o->c, G + o->oW3, G + o->ob3, B, H1, H2, br, sB))) return rc;
         if ((rc = launch_dense_bwd_x(o->dz3, W3, o->a2, drop, o->dz2, B, H1, H2, 1, br, st))) return rc;
-        if ((rc = launch_dense_bwd_w(o->dz2, o->a1, G + o->oW2, G + o->ob2, B, H2, H1, br, st))) return rc;
+        if ((rc = fork(st, sC))) return rc;
+        if ((rc = launch_dense_bwd_w(o->dz2, o->a1, G + o->oW2, G + o->ob2, B, H2, H1, br, sC))) return rc;
         if ((rc = launch_dense_bwd_x(o->dz2, W2, o->a1, nodrop, o->dz1, B, H2, H1, 1, br, st))) return rc;
     }
-    // dW1t: segmented over (batch, data column); db1 = column sums of dZ1
+    // dW1t: segmented over (batch, data column) on the main stream; db1 = column sums of dZ1 on branch B
     if (WANT(K_SEG_W1)) {
+        if ((rc = fork(st, sB))) return rc;
+        if ((rc = launch_colsum(o->dz1, H1, G + o->ob1, br, sB))) return rc;
         ChunkedSegs cs{o->pd.perm, o->pd.ent_row, o->pd.seg_key, o->pd.seg_off, o->pd.batch_seg_off,
                        o->pd.seg_chunk_off, o->pd.chunk_seg, o->pd.batch_chunk_off, o->pd.part, o->pd.part_bias, b,
                        o->n_enc};
         if ((rc = launch_segment_chunks(cs, o->n_enc * 2, o->n_enc, o->dval_ord, o->dz1, H1, G + o->oW1, nullptr,
                                         o->active, st)))
             return rc;
-        if ((rc = launch_colsum(o->dz1, H1, G + o->ob1, br, st))) return rc;
     }
+    // join: the norm reads every gradient
+    if ((rc = fork(sA, st)) || (rc = fork(sB, st)) || (rc = fork(sC, st))) return rc;
     // clip + Adam
     if (WANT(K_NORM))
         if ((rc = launch_sqnorm_stage1(G, o->n_params, o->partial, br, st))) return rc;
@@ -454,6 +482,8 @@ static int free_all(dmt_org* o) {
     cudaFree(o->rows_buf); cudaFree(o->row_off_buf); cudaFree(o->keep_buf); cudaFree(o->seed_dev);
     cudaFree(o->loss_buf); cudaFree(o->partial); cudaFree(o->sc); cudaFree(o->step_dev);
     if (o->ev) cudaEventDestroy(o->ev);
+    for (int i = 0; i < 3; ++i) if (o->aux[i]) cudaStreamDestroy(o->aux[i]);
+    for (int i = 0; i < kForkEvents; ++i) if (o->fev[i]) cudaEventDestroy(o->fev[i]);
     if (o->own_stream && o->st) cudaStreamDestroy(o->st);
     return 0;
 }
@@ -542,6 +572,9 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
 #undef A
     {
         cudaError_t e = cudaEventCreateWithFlags(&o->ev, cudaEventDisableTiming);
+        for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&o->aux[i], cudaStreamNonBlocking);
+        for (int i = 0; i < kForkEvents && e == cudaSuccess; ++i)
+            e = cudaEventCreateWithFlags(&o->fev[i], cudaEventDisableTiming);
         if (e != cudaSuccess) { free_all(o); delete o; set_error(cudaGetErrorString(e)); return (int)e; }
     }
     iota32_kernel<<<(n_rows + 255) / 256, 256, 0, o->st>>>(o->iota_rows, n_rows);

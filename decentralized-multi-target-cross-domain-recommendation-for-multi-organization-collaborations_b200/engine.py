@@ -176,8 +176,10 @@ class FastEpochLayout:
 
 
 def decoder_default():
-    """Decoder form of new engines: DMT_DECODER=gather|tc (default tc: tcgen05 GEMMs, 3xTF32)."""
-    mode = os.environ.get("DMT_DECODER", "tc")
+    """Decoder form of new engines: DMT_DECODER=gather|tc. Default gather (row-gather SDDMM + segmented reductions):
+    measured on B200 at ML1M shape (500-row batches, 3.7 % dense targets) it is ~1.5x faster per step than the
+    tcgen05 GEMMs with the 3xTF32 parity split; tc pays off for denser / larger batches."""
+    mode = os.environ.get("DMT_DECODER", "gather")
     if mode not in ("tc", "gather"):
         raise ValueError("Not valid DMT_DECODER: {}".format(mode))
     return mode

@@ -48,6 +48,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s (burst figure: the kernel is timed alone)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured bf16 burst (MEASURED_PEAKS.json)"
+    return 1590.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe's clocks line)."""
 
@@ -236,6 +245,11 @@ def run_ours(args):
                 "step_kernel_ms": prof, "slowest_class": dom,
                 "adam_GBps": n_params * 28 / (prof["clip_adam"] * 1e-3) / 1e9}
         roof["hbm_case"] = hbm_bound_case(dev, hbm)
+        # the decoder's other form (tcgen05 GEMMs, 3xTF32): same batch, same plan, per-class timings + D1 alone
+        eng.set_decoder("tc")
+        prof_tc = eng.h.profile_step(b=0, reps=20)
+        eng.set_decoder(E.decoder_default() if eng.target.sorted else "gather")
+        roof["tc_decoder"] = tc_decoder_case(rounds.state.y["train"], dev, prof, prof_tc)
 
     # ---- end to end through the drop-in API with host buffers (single-process API: measured on rank 0's GPU)
     e2e = run_e2e(args, data, rank, world, dev)
@@ -259,6 +273,8 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "control_name": CONTROL, "local_epochs": args.local_epochs,
                        "orgs_per_rank": len(rounds.my_orgs), "parallelism": "org-sharded x{}".format(world),
+                       "decoder": rounds.eng[rounds.my_orgs[0]].decoder if rounds.my_orgs else None,
+                       "step_fanout": bool(rounds.fanout),
                        "l2_policy": "inputs larger than L2: per-round working set (18 x 17 MB parameters+moments, "
                                     "2 x 72 MB prediction matrices, plans) exceeds 126 MB"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
@@ -319,6 +335,63 @@ def hbm_bound_case(dev, hbm):
             "ms_per_launch": ms, "algorithmic_bytes_per_launch": bytes_, "achieved": ach, "peak": hbm,
             "frac": ach / hbm, "unit": "GB/s",
             "traffic": 1.101e9, "traffic_source": "profiles/r1_ncu_raw_decoder_hbm.csv: dram read 1.088 GB + write 13 MB per launch"}
+
+
+def tc_decoder_case(y_csr, dev, prof_gather, prof_tc):
+    """The tensor-core form of the decoder's last layer (csrc/decoder_tc.cu; tcgen05.mma kind::tf32, 3xTF32 parity
+    split) on one real ML1M-shape batch — the first 500 rows of the train target CSR: the forward GEMM + masked
+    epilogue (D1) alone through the raw C-ABI with preallocated outputs, CUDA events on the launching stream. Tensor
+    roofline: ALGORITHMIC flops 2*B*N*H (one fp32 product; the three TF32 passes are the price of parity, not work)
+    against the measured dense bf16 peak; TF32 runs at half the bf16 rate, so 1/6 of that peak is this kernel's
+    ceiling. Next to it the engine's per-class step timings in both decoder modes (same batch, same plan)."""
+    from dmtcdr_b200 import native
+
+    lib = native.load()
+    n_rows, H = 500, 256
+    n_dec = y_csr.shape[1]
+    nnz = int(y_csr.indptr_host[n_rows])
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    A3 = torch.tanh(torch.randn(n_rows, H, device=dev, generator=g))
+    W4 = torch.empty(n_dec, H, device=dev).normal_(0, 0.05, generator=g)
+    b4 = torch.zeros(n_dec, device=dev)
+    rows = torch.arange(n_rows, device=dev, dtype=torch.int32)
+    pred = torch.empty(y_csr.nnz, device=dev)
+    scratch = torch.empty(lib.dmt_ae_decoder_tc_scratch_floats(n_rows, n_dec, H), device=dev)
+    P = native.ptr
+
+    def launch(passes):
+        native.check(lib.dmt_ae_decoder_tc(P(rows), n_rows, P(y_csr.indptr), P(y_csr.indices), None, P(A3), P(W4), P(b4),
+                                           H, n_dec, 0, None, passes, P(pred), None, None, None, None, None, 0,
+                                           P(scratch), native.stream()), "dmt_ae_decoder_tc")
+
+    out = {}
+    for passes in (3, 1):
+        for _ in range(3):
+            launch(passes)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            launch(passes)
+        e1.record()
+        torch.cuda.synchronize()
+        out[passes] = e0.elapsed_time(e1) / reps
+    flops = 2.0 * n_rows * n_dec * H
+    peak, src = measured_tensor_peak()
+    ach = flops / (out[3] * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "tile_tab_kernel + dec_fwd_tc_kernel (D1: A3 W4^T on tcgen05, masked epilogue)",
+            "shape": "{} rows x {} items x H {} ({} targets, {:.1f} % dense)".format(n_rows, n_dec, H, nnz,
+                                                                                   100.0 * nnz / (n_rows * n_dec)),
+            "ms_per_launch_3xTF32": out[3], "ms_per_launch_1xTF32": out[1],
+            "algorithmic_flops_per_launch": flops, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": src,
+            "tensor_pipe_source": "profiles/r1_ncu_raw_tc.csv: sm__pipe_tensor_cycles_active 20 % (D1), 13 % (D2), "
+                                  "18 % (D3) of peak sustained active",
+            "step_kernel_ms_gather": {k: prof_gather[k] for k in ("decoder_loss_dz3", "dw4_segments")},
+            "step_kernel_ms_tc": {k: prof_tc[k] for k in ("decoder_loss_dz3", "dw4_segments")},
+            "note": "latency-bound at this size (116 CTAs x 8 k-chunks); the gather form stays the engine default at "
+                    "ML1M shape (DESIGN.md section 5)"}
 
 
 def run_mf_joint(data, dev, epochs=3):

@@ -76,6 +76,7 @@ struct dmt_org {
     int64_t dec_chunk_cap, dec_part_rows;
     // tensor-core decoder (decoder_tc.cu)
     int dec_mode, dec_passes;
+    int fanout;  // 1: the backward pass of a step is enqueued as parallel branches (dmt_org_set_fanout)
     float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
     // tables of per-row CSR windows at 128-column tile borders, one per target CSR seen (train targets, predict splits)
     struct TabEntry { const int32_t *indptr, *indices; int n_rows; int32_t* tab; };
@@ -381,7 +382,7 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
     // organization's auxiliary streams between event forks/joins; under stream capture they become parallel branches
     // of the epoch graph, so a step's critical path is the dZ2 -> dZ1 -> dW1 chain instead of the sum of all kernels.
     // (`only` >= 0, the per-class profiler, keeps everything on the main stream.)
-    const bool par = only < 0;
+    const bool par = only < 0 && o->fanout != 0;
     cudaStream_t sA = par ? o->aux[0] : st, sB = par ? o->aux[1] : st, sC = par ? o->aux[2] : st;
     int ev_i = 0;
     auto fork = [&](cudaStream_t from, cudaStream_t to) -> int {  // `to` continues after everything enqueued on `from`
@@ -597,6 +598,18 @@ int dmt_org_destroy(dmt_org_t* o) {
 }
 
 int64_t dmt_org_num_params(const dmt_org_t* o) { return o ? o->n_params : 0; }
+
+int dmt_org_set_fanout(dmt_org_t* o, int on) {
+    DMT_REQUIRE(o, "dmt_org_set_fanout: null");
+    on = on ? 1 : 0;
+    if (o->fanout != on && o->exec) {  // the shape of the graph changes
+        cudaGraphExecDestroy(o->exec);
+        o->exec = nullptr;
+        o->g_nb = -1;
+    }
+    o->fanout = on;
+    return 0;
+}
 
 int dmt_org_set_decoder_mode(dmt_org_t* o, int mode, int passes) {
     DMT_REQUIRE(o && (mode == 0 || mode == 1) && (passes == 1 || passes == 3), "dmt_org_set_decoder_mode: bad argument");

@@ -80,6 +80,7 @@ def _declare(lib):
         "dmt_ae_decoder_tc_scratch_floats": (L, [I, I, I]),
         "dmt_ae_decoder_tc": (I, [P, I, P, P, P, P, P, P, I, I, I, P, I, P, P, P, P, P, P, I, P, P]),
         "dmt_org_set_decoder_mode": (I, [P, I, I]),
+        "dmt_org_set_fanout": (I, [P, I]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
         "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, I, P]),
         "dmt_org_create": (I, [C.POINTER(P), I, I, I, I, I, P, P, P, L, P, P, L, I, I, I, P]),
@@ -495,6 +496,10 @@ class Org:
         code = {"gather": 0, "tc": 1}[mode]
         check(self._lib.dmt_org_set_decoder_mode(self.h, code, int(passes)), "dmt_org_set_decoder_mode")
         self.decoder_mode = mode
+
+    def set_fanout(self, on):
+        """Backward pass of a step as parallel graph branches (pays with few organizations per GPU)."""
+        check(self._lib.dmt_org_set_fanout(self.h, int(bool(on))), "dmt_org_set_fanout")
 
     def set_params(self, flat):
         check(self._lib.dmt_org_set_params(self.h, ptr(flat)), "dmt_org_set_params")

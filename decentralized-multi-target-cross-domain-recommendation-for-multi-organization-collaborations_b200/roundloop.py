@@ -10,12 +10,19 @@ rank runs the same (cheap, O(K nnz)) ``update`` so F_{t} is replicated without a
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import engine as E
 from . import native
+
+
+# organizations per GPU up to which a step's backward pass is enqueued as parallel graph branches (dmt_org_set_fanout);
+# DMT_FANOUT=0|1 overrides. Measured on one B200 at ML1M shape, ms per round without -> with: 3 organizations 72.9 -> 63.3,
+# 5: 96.1 -> 85.5, 9: 140.4 -> 130.7, 18: 271 -> 301 (their graphs already fill the machine).
+FANOUT_MAX_ORGS = 9
 
 
 def xavier_uniform_(shape, device, generator=None):
@@ -70,6 +77,11 @@ class AssistRounds:
         # optional lockstep group: one launch per step kernel for ALL organizations of this rank (dmt_group_*).
         # Measured on B200 at ML1M shape (18 organizations): 281 ms/round against 257 ms for per-organization graphs
         # on private streams — both are bound by the same L2 gather traffic — so per-organization graphs stay default.
+        fan = os.environ.get("DMT_FANOUT")
+        fan = (len(self.my_orgs) <= FANOUT_MAX_ORGS) if fan is None else fan == "1"
+        for k in self.my_orgs:
+            self.eng[k].h.set_fanout(fan)
+        self.fanout = fan
         self.group = native.Group([self.eng[k].h for k in self.my_orgs]) if group and self.my_orgs else None
         self.cols = cols
         self.mats = mats

@@ -221,6 +221,12 @@ int dmt_org_destroy(dmt_org_t* org);
  * reductions (any CSR), mode 1 = tcgen05 GEMMs (dmt_ae_decoder_tc; needs ascending column indices inside every row of
  * the target CSR and of the CSRs passed to dmt_org_predict). passes: 3 (3xTF32, parity mode) or 1. Default: mode 0. */
 int dmt_org_set_decoder_mode(dmt_org_t* org, int mode, int passes);
+/* Shape of a training step inside the epoch graph. on = 0 (default): one chain of kernels. on != 0: after the decoder
+ * the backward pass is enqueued as the DAG it is ({dW4,db4} | {dW3,db3} | dZ2 -> ({dW2,db2} | dZ1 -> (dW1 | db1)))
+ * on auxiliary streams, i.e. parallel branches of the captured graph: a shorter critical path per step, which pays
+ * when a GPU holds few organizations (org-sharded runs); with many organizations per GPU their graphs already fill the
+ * machine and the extra cross-branch dependencies cost more than they save (measured). Same results. */
+int dmt_org_set_fanout(dmt_org_t* org, int on);
 /* number of fp32 parameters; flat layout: W1t[n_enc*H1] b1[H1] W2[H2*H1] b2[H2] W3[H1*H2] b3[H1] W4[n_dec*H1] b4[n_dec] */
 int64_t dmt_org_num_params(const dmt_org_t* org);
 /* Copy parameters in/out (device pointers, flat layout above). set also resets the Adam state: the reference builds

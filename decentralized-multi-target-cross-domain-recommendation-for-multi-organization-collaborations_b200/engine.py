@@ -291,9 +291,44 @@ class MtalState:
         self.O_full = {k: torch.zeros(max(self.K, o_rows or 0), self.y[k].nnz, device=device) for k in y}
         self.O = {k: self.O_full[k][:self.K] for k in y}
         self._views = {}
+        self._eval_meta = {}
 
     def residual(self, F, split, clamp, out=None):
         return native.residual(F, self.y[split].data, self.loss_kind, 1.0 if clamp else 0.0, out)
+
+    def evaluate(self, F, split="test", block_rows=500, topk=10):
+        """Global metrics of the current prediction with the reference's test loop semantics
+        (src/train_recsys_assist.py:175-217, src/logger.py:35-55) computed on the device: per-block Loss and
+        RMSE (explicit) or NDCG@topk (implicit), entry-weighted over blocks. One launch + a [n_blocks x 3] read-back."""
+        y = self.y[split]
+        n_rows = y.shape[0]
+        key = (split, block_rows, topk)
+        if key not in self._eval_meta:
+            ip = y.indptr_host
+            edges = np.arange(0, n_rows + block_rows, block_rows).clip(max=n_rows)
+            m = (ip[edges[1:]] - ip[edges[:-1]]).astype(np.float64)          # entries per block
+            rl = np.diff(ip) > 0
+            rows_nz = np.add.reduceat(rl, edges[:-1]).astype(np.float64) if n_rows else np.zeros(0)
+            k = np.array([min(topk, len(np.unique(y.indices_host[ip[a]:ip[b]]))) for a, b in zip(edges[:-1], edges[1:])],
+                         dtype=np.int32)
+            self._eval_meta[key] = (m, rows_nz, to_dev(k, self.device))
+        m, rows_nz, k_dev = self._eval_meta[key]
+        implicit = self.target_mode == "implicit"
+        sums = to_host(native.eval_blocks(y.indptr, F, y.data, n_rows, block_rows, self.loss_kind,
+                                          k_dev if implicit else None)).double().numpy()
+        ok = m > 0
+        w = m[ok] / m[ok].sum()
+        out = {"{}/Loss".format(split): float((sums[ok, 0] / m[ok] * w).sum())}
+        if implicit:
+            out["{}/NDCG".format(split)] = float((sums[ok, 2] / rows_nz[ok] * w).sum())
+        else:
+            out["{}/RMSE".format(split)] = float((np.sqrt(sums[ok, 1] / m[ok]) * w).sum())
+        return out
+
+    def privatize(self, residual, mode, param, seed):
+        """make_privacy (src/privacy.py) on the device, in place on a residual vector (production mode)."""
+        native.privacy(residual, mode, param, seed, out=residual)
+        return residual
 
     def owner_view(self, split, i):
         """Static per-owner view for the fit: positions of the owner's entries sorted by local column (stable),

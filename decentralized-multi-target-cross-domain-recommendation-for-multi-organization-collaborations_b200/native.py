@@ -83,6 +83,9 @@ def _declare(lib):
         "dmt_org_set_fanout": (I, [P, I]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
         "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, I, P]),
+        "dmt_eval_blocks": (I, [P, P, P, I, I, I, I, P, P, P]),
+        "dmt_privacy_temp_bytes": (L, [L]),
+        "dmt_privacy": (I, [P, L, I, F, C.c_uint64, P, P, P, L, P]),
         "dmt_org_create": (I, [C.POINTER(P), I, I, I, I, I, P, P, P, L, P, P, L, I, I, I, P]),
         "dmt_group_create": (I, [C.POINTER(P), C.POINTER(P), I, P]),
         "dmt_group_destroy": (I, [P]),
@@ -429,6 +432,28 @@ def ae_decoder_fwd(rows, indptr, indices, target, A3, W4, b4, loss_kind, nnz, tr
                                     ptr(b4), H, loss_kind, ptr(n_t), ptr(pred), ptr(gout), ptr(dz3), ptr(loss_rows),
                                     int(bool(tanh_deriv)), stream()), "dmt_ae_decoder_fwd")
     return pred, gout, dz3, loss_rows, n_t
+
+
+def eval_blocks(indptr, pred, target, n_rows, block_rows, loss_kind, block_k=None):
+    """Per-block sums [n_blocks x 3] = (loss, squared error, sum of per-row NDCG) — dmt_eval_blocks."""
+    n_blocks = (n_rows + block_rows - 1) // block_rows
+    out = torch.zeros(n_blocks, 3, device=pred.device, dtype=torch.float32)
+    check(load().dmt_eval_blocks(ptr(indptr), ptr(pred), ptr(target), n_rows, block_rows, loss_kind,
+                                 int(block_k is not None), ptr(block_k), ptr(out), stream()), "dmt_eval_blocks")
+    return out
+
+
+def privacy(y, mode, param, seed, out=None):
+    """make_privacy on the device (dmt_privacy). Returns (perturbed vector, [a, b] quantile pair)."""
+    lib = load()
+    n = y.numel()
+    out = torch.empty_like(y) if out is None else out
+    q = torch.empty(2, device=y.device, dtype=torch.float32)
+    nbytes = lib.dmt_privacy_temp_bytes(n)
+    temp = torch.empty(nbytes, device=y.device, dtype=torch.uint8)
+    check(lib.dmt_privacy(ptr(y), n, {"dp": 0, "ip": 1}[mode], float(param), int(seed) & (2 ** 64 - 1), ptr(out), ptr(q),
+                          ptr(temp), nbytes, stream()), "dmt_privacy")
+    return out, q
 
 
 class Group:

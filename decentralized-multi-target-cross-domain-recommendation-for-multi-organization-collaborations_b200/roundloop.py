@@ -47,13 +47,14 @@ def init_flat_params(n_enc, n_dec, H1, H2, device, generator=None):
 class AssistRounds:
     def __init__(self, mats, data_split, target_mode, batch_rows, clamp=False, ar=0.1, ar_mode="constant",
                  aw_mode="constant", match_rate=1.0, local_epochs=20, rank=0, world=1, device="cuda", H1=256, H2=128,
-                 seed=0, hp=None, group=False):
+                 seed=0, hp=None, group=False, privacy=None):
         """mats: {'train': (data_csr, target_csr), 'test': (...)} global scipy CSR matrices (rows = aligned entity)."""
         self.rank, self.world, self.device = rank, world, device
         self.K = len(data_split)
         self.target_mode, self.clamp = target_mode, clamp
         self.ar, self.ar_mode, self.aw_mode, self.match_rate = ar, ar_mode, aw_mode, match_rate
         self.local_epochs, self.batch_rows, self.seed = local_epochs, batch_rows, seed
+        self.privacy = privacy  # None or (mode 'dp'|'ip', param): device-side make_privacy on the broadcast residuals
         self.H1, self.H2 = H1, H2
         self.hp = hp or dict(lr=1e-3, betas=(0.9, 0.999), weight_decay=5e-4, max_norm=1.0)
         self.splits = list(mats)
@@ -142,8 +143,10 @@ class AssistRounds:
         """Rank-local part of a round. Parameter init, sampler permutations and the dropout stream are seeded per
         (seed, organization, round), so the result does not depend on how organizations are sharded over ranks."""
         st = self.state
-        for k in self.splits:
+        for i, k in enumerate(self.splits):
             st.residual(self.F[k], k, self.clamp, out=self.residual[k])
+            if self.privacy is not None:  # src/assist.py:59-60; same noise on every rank (seeded by round and split)
+                st.privatize(self.residual[k], self.privacy[0], self.privacy[1], E.he_seed(self.seed, t, i, 1 << 22))
         loss_bufs = {}
         layouts, rows_dev, off_dev = {}, {}, {}
         for org in self.my_orgs:
@@ -213,6 +216,10 @@ class AssistRounds:
         F_next, fitted = self.state.update(self.F, self.ar, self.ar_mode, self.aw_mode, self.match_rate)
         self.F = F_next
         return F_next, fitted
+
+    def evaluate(self, split="test"):
+        """Test metrics of the current global prediction F_t, computed on the device (MtalState.evaluate)."""
+        return self.state.evaluate(self.F[split], split, self.batch_rows)
 
     def sync(self):
         for eng in self.eng.values():

@@ -201,6 +201,26 @@ int dmt_ae_decoder_tc(const int32_t* rows, int n_rows, const int32_t* indptr, co
                       int loss_kind, const int32_t* n_targets, int passes, float* pred, float* gout, float* dZ3,
                       float* dW4, float* db4, float* loss_rows, int tanh_deriv, float* scratch, void* stream);
 
+/* ------------------------------------------------------------------ evaluation and privacy */
+
+/* Global test metrics of src/train_recsys_assist.py:175-217 on the device: the split (CSR rows, pred/target aligned
+ * with its storage order) is walked in blocks of block_rows rows; out[3*b + {0,1,2}] = sum of the loss
+ * (src/models/utils.py:7-14), sum of squared errors (RMSE, src/metrics/metrics.py:8-11) and sum over the block's
+ * non-empty rows of DCG@k/IDCG@k (src/metrics/metrics.py:63-84; unobserved columns rank last with gain 0, k =
+ * block_k[b] = min(topk, #distinct columns of the block); want_ndcg = 0 skips it). The caller divides by the block's
+ * entry / row counts and forms the entry-weighted mean over blocks (src/logger.py:35-55). No atomics: reproducible. */
+int dmt_eval_blocks(const int32_t* indptr, const float* pred, const float* target, int n_rows, int block_rows,
+                    int loss_kind, int want_ndcg, const int32_t* block_k, float* out, void* stream);
+
+/* make_privacy of src/privacy.py:6-58 (applied to the pseudo-residuals at src/assist.py:59-60): clip range [a, b] =
+ * the 2.5 % / 97.5 % quantiles of y (numpy's linear interpolation), mode 0 = dp: clip(y) + Laplace((b-a)/param),
+ * mode 1 = ip: mean over int(param) uniform thresholds t of (2t-b if y<t else 2t-a). Noise: counter-based generator
+ * keyed on (seed, element, draw) — reproducible, but NOT numpy's stream (the host path replays that). out may alias y.
+ * quantiles (may be NULL) receives a, b. temp >= dmt_privacy_temp_bytes(n) bytes. */
+int64_t dmt_privacy_temp_bytes(int64_t n);
+int dmt_privacy(const float* y, int64_t n, int mode, float param, uint64_t seed, float* out, float* quantiles,
+                void* temp, int64_t temp_bytes, void* stream);
+
 /* ------------------------------------------------------------------ device-resident organization engine */
 
 typedef struct dmt_org dmt_org_t;

@@ -7,8 +7,10 @@ import dmtcdr_b200
 from dmtcdr_b200 import roundloop
 
 epochs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+group = len(sys.argv) > 2 and sys.argv[2] == "group"
 data, dataset, data_split, mats, cfg = bench.build_problem()
-R = roundloop.AssistRounds(mats, [s.numpy() for s in data_split], "explicit", 500, local_epochs=epochs, device="cuda:0")
+R = roundloop.AssistRounds(mats, [s.numpy() for s in data_split], "explicit", 500, local_epochs=epochs, device="cuda:0",
+                           group=group)
 R.round0()
 for t in (1, 2):
     R.run_round(t)

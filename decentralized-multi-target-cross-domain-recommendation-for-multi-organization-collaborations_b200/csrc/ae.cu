@@ -226,14 +226,18 @@ __device__ __forceinline__ void ae_decoder_chunk_body(const int32_t* __restrict_
                                                               float* __restrict__ gout, BatchRef br) {
     constexpr int H = VEC * 128;
     constexpr int PER_WARP = kDecChunk / 8;  // 16 targets per warp
-    __shared__ float s_acc[8][H];
-    __shared__ float s_loss[8];
+    constexpr int GROUPS = PER_WARP / 4;     // in groups of four 1 KB weight rows
+    // double-buffered so that a chunk needs ONE block barrier: the next chunk's partials go to the other buffer, and
+    // nobody can be two chunks ahead of a thread that still reads (it would have to pass the barrier in between)
+    __shared__ float s_acc[2][8][H];
+    __shared__ float s_loss[2][8];
     int lo, hi;
     if (!batch_range(br, lo, hi)) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c_lo = dc.batch_chunk_off[br.b], c_hi = dc.batch_chunk_off[br.b + 1];
     const float inv_n = 1.f / (float)n_targets[br.b];
-    for (int c = c_lo + blockIdx.x; c < c_hi; c += gridDim.x) {
+    int buf = 0;
+    for (int c = c_lo + blockIdx.x; c < c_hi; c += gridDim.x, buf ^= 1) {
         const int j = dc.chunk_row[c];  // epoch-wide batch-row index
         const int u = rows[j];
         const int k = c - dc.chunk_off[j];
@@ -258,55 +262,53 @@ __device__ __forceinline__ void ae_decoder_chunk_body(const int32_t* __restrict_
             y_l = target[eb + lane];
         }
         float o_l = 0.f;
-        int i = 0;
-        for (; i + 4 <= cnt; i += 4) {  // four 1 KB weight rows in flight per warp
-            int cc[4];
-            float4 w[4][VEC];
+        if (cnt > 0) {
+            // software pipeline: the four weight rows of group g+1 are in flight while group g is reduced, so eight 1 KB
+            // rows per warp are outstanding instead of a load-wait-compute sequence per group. Slots past `cnt` re-read
+            // the last valid row and contribute with g = 0.
+            float4 w[2][4][VEC];
+            float bb[2][4];
+            auto load_group = [&](int g, int slot) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cc[q] = __shfl_sync(0xffffffffu, c_l, i + q);
+                for (int q = 0; q < 4; ++q) {
+                    const int col = __shfl_sync(0xffffffffu, c_l, min(4 * g + q, cnt - 1));
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) w[q][v] = ld4(W4 + (int64_t)cc[q] * H + v * 128 + lane * 4);
-            float d[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                d[q] = 0.f;
-#pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    d[q] += a[v].x * w[q][v].x + a[v].y * w[q][v].y + a[v].z * w[q][v].z + a[v].w * w[q][v].w;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                d[q] = warp_sum(d[q]) + b4[cc[q]];
-                if (lane == i + q) o_l = d[q];
-                const float g = loss_grad(loss_kind, d[q], __shfl_sync(0xffffffffu, y_l, i + q)) * inv_n;
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    acc[v].x = fmaf(g, w[q][v].x, acc[v].x);
-                    acc[v].y = fmaf(g, w[q][v].y, acc[v].y);
-                    acc[v].z = fmaf(g, w[q][v].z, acc[v].z);
-                    acc[v].w = fmaf(g, w[q][v].w, acc[v].w);
+                    for (int v = 0; v < VEC; ++v) w[slot][q][v] = ld4(W4 + (int64_t)col * H + v * 128 + lane * 4);
+                    bb[slot][q] = b4[col];
                 }
-            }
-        }
-        for (; i < cnt; ++i) {
-            const int c0 = __shfl_sync(0xffffffffu, c_l, i);
-            float4 w0[VEC];
+            };
+            load_group(0, 0);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) w0[v] = ld4(W4 + (int64_t)c0 * H + v * 128 + lane * 4);
-            float d0 = 0.f;
+            for (int g = 0; g < GROUPS; ++g) {
+                if (4 * g < cnt) {  // warp-uniform
+                    const int slot = g & 1;
+                    if (g + 1 < GROUPS && 4 * (g + 1) < cnt) load_group(g + 1, (g + 1) & 1);
+                    float d[4];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) d0 += a[v].x * w0[v].x + a[v].y * w0[v].y + a[v].z * w0[v].z + a[v].w * w0[v].w;
-            d0 = warp_sum(d0) + b4[c0];
-            if (lane == i) o_l = d0;
-            const float g = loss_grad(loss_kind, d0, __shfl_sync(0xffffffffu, y_l, i)) * inv_n;
+                    for (int q = 0; q < 4; ++q) {
+                        d[q] = 0.f;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                acc[v].x = fmaf(g, w0[v].x, acc[v].x);
-                acc[v].y = fmaf(g, w0[v].y, acc[v].y);
-                acc[v].z = fmaf(g, w0[v].z, acc[v].z);
-                acc[v].w = fmaf(g, w0[v].w, acc[v].w);
+                        for (int v = 0; v < VEC; ++v)
+                            d[q] += a[v].x * w[slot][q][v].x + a[v].y * w[slot][q][v].y + a[v].z * w[slot][q][v].z +
+                                    a[v].w * w[slot][q][v].w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int t = 4 * g + q;
+                        const bool valid = t < cnt;
+                        d[q] = warp_sum(d[q]) + bb[slot][q];
+                        if (lane == t && valid) o_l = d[q];
+                        const float y = __shfl_sync(0xffffffffu, y_l, min(t, cnt - 1));
+                        const float gq = valid ? loss_grad(loss_kind, d[q], y) * inv_n : 0.f;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            acc[v].x = fmaf(gq, w[slot][q][v].x, acc[v].x);
+                            acc[v].y = fmaf(gq, w[slot][q][v].y, acc[v].y);
+                            acc[v].z = fmaf(gq, w[slot][q][v].z, acc[v].z);
+                            acc[v].w = fmaf(gq, w[slot][q][v].w, acc[v].w);
+                        }
+                    }
+                }
             }
         }
         if (lane < cnt) {
@@ -314,24 +316,23 @@ __device__ __forceinline__ void ae_decoder_chunk_body(const int32_t* __restrict_
             loss_acc = loss_value(loss_kind, o_l, y_l);
         }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) st4(&s_acc[wid][v * 128 + lane * 4], acc[v]);
+        for (int v = 0; v < VEC; ++v) st4(&s_acc[buf][wid][v * 128 + lane * 4], acc[v]);
         loss_acc = warp_sum(loss_acc);
-        if (lane == 0) s_loss[wid] = loss_acc;
+        if (lane == 0) s_loss[buf][wid] = loss_acc;
         __syncthreads();
-        const int64_t slot = c - c_lo;
+        const int64_t slot_out = c - c_lo;
         for (int h = threadIdx.x; h < H; h += 256) {
             float s = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) s += s_acc[w8][h];
-            dc.dz_part[slot * H + h] = s;
+            for (int w8 = 0; w8 < 8; ++w8) s += s_acc[buf][w8][h];
+            dc.dz_part[slot_out * H + h] = s;
         }
         if (threadIdx.x == 0) {
             float l = 0.f;
 #pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) l += s_loss[w8];
-            dc.loss_part[slot] = l;
+            for (int w8 = 0; w8 < 8; ++w8) l += s_loss[buf][w8];
+            dc.loss_part[slot_out] = l;
         }
-        __syncthreads();
     }
 }
 

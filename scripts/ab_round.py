@@ -12,9 +12,10 @@ from dmtcdr_b200 import roundloop
 n_rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 world = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+group = len(sys.argv) > 4 and sys.argv[4] == "group"
 data, dataset, data_split, mats, cfg = bench.build_problem()
 R = roundloop.AssistRounds(mats, [s.numpy() for s in data_split], "explicit", 500, local_epochs=epochs, device="cuda:0",
-                           rank=0, world=world)
+                           rank=0, world=world, group=group)
 R.round0()
 
 
@@ -37,6 +38,6 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n_rounds
 eng = R.eng[R.my_orgs[0]]
 prof = eng.h.profile_step(b=0, reps=20)
-print(json.dumps({"decoder": eng.decoder, "fanout": R.fanout, "world": world, "orgs": len(R.my_orgs), "ms_per_round": ms,
+print(json.dumps({"decoder": eng.decoder, "fanout": R.fanout, "group": group, "world": world, "orgs": len(R.my_orgs), "ms_per_round": ms,
                   "step_kernel_ms_org0": {k: round(v, 5) for k, v in prof.items()},
                   "step_sum_us": 1e3 * sum(prof.values())}))

@@ -19,6 +19,8 @@ from dmtcdr_b200.config import cfg
 import models
 
 _DEVICE_CSR = {}
+import os as _os
+_NO_FASTPATH = _os.environ.get("DMT_NO_FASTPATH") == "1"
 _CSR_IDENTITY = {}  # (id(indptr), id(indices)) -> (indptr, indices, shape, nnz, content key)
 
 
@@ -26,6 +28,8 @@ def _structure_key(m):
     """Content key of the CSR structure. CRC-ing the index arrays costs ~1 ms per call at ML1M shape and the drivers
     hand the same arrays back ~100 times per round, so the arrays' identity is tried first; the cache holds references
     to them, which keeps their ids unique for as long as an entry lives."""
+    if _NO_FASTPATH:
+        return E.csr_key(m)
     ip, ix = m.indptr, m.indices
     fk = (id(ip), id(ix))
     ent = _CSR_IDENTITY.get(fk)

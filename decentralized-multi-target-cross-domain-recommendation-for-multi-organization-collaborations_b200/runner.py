@@ -184,14 +184,25 @@ def run_assist_experiment(data, control_name, seed=0, local_epochs=None, rounds=
     initialize(dataset, assist, organization, metric, logger)
     metrics = {0: evaluate(assist, metric, logger, 0)}
     logger.reset()
+    import os, time
+    trace = os.environ.get('DMT_TRACE') == '1'
     for t in range(1, cfg['global']['num_epochs'] + 1):
+        tm = [time.perf_counter()]
         dataset = assist.make_dataset(dataset, t)
+        tm.append(time.perf_counter())
         for i in range(len(organization)):
             organization[i].train(dataset[i]['train'], metric, logger, t)
+        tm.append(time.perf_counter())
         outs = [{k: organization[i].predict(dataset[i][k], t) for k in dataset[i]} for i in range(len(dataset))]
+        tm.append(time.perf_counter())
         assist.update(outs, t)
+        tm.append(time.perf_counter())
         metrics[t] = evaluate(assist, metric, logger, t)
+        tm.append(time.perf_counter())
         logger.reset()
+        if trace:
+            names = ['make_dataset', 'train', 'predict', 'update', 'evaluate']
+            print('round', t, {n: round(1e3 * (b - a), 1) for n, a, b in zip(names, tm[:-1], tm[1:])}, flush=True)
         if on_round is not None:
             on_round(t)
     res = {'F': [{k: m[k].data.copy() for k in m} for m in assist.organization_output], 'metrics': metrics,

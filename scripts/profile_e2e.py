@@ -13,9 +13,13 @@ def on_round(t):
     torch.cuda.synchronize()
     marks.append(time.perf_counter())
 pr = cProfile.Profile()
+use_prof = os.environ.get("E2E_PROFILE", "1") == "1"
 def run():
     return runner.run_assist_experiment(data, bench.CONTROL, seed=0, local_epochs=20, rounds=n, rng="device", on_round=on_round)
-pr.enable(); res = run(); pr.disable()
+if use_prof:
+    pr.enable()
+res = run()
+pr.disable()
 print("round ms:", [round(1e3 * (b - a), 1) for a, b in zip(marks[:-1], marks[1:])])
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)

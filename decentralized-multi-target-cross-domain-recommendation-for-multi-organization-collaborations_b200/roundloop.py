@@ -23,6 +23,8 @@ from . import native
 # DMT_FANOUT=0|1 overrides. Measured on one B200 at ML1M shape, ms per round without -> with: 3 organizations 72.9 -> 63.3,
 # 5: 96.1 -> 85.5, 9: 140.4 -> 130.7, 18: 271 -> 301 (their graphs already fill the machine).
 FANOUT_MAX_ORGS = 9
+# device memory the whole-round plans of a rank may take (bytes); DMT_WHOLE_ROUND=0|1 overrides
+WHOLE_ROUND_PLAN_BUDGET = 48 << 30
 
 
 def xavier_uniform_(shape, device, generator=None):
@@ -47,7 +49,7 @@ def init_flat_params(n_enc, n_dec, H1, H2, device, generator=None):
 class AssistRounds:
     def __init__(self, mats, data_split, target_mode, batch_rows, clamp=False, ar=0.1, ar_mode="constant",
                  aw_mode="constant", match_rate=1.0, local_epochs=20, rank=0, world=1, device="cuda", H1=256, H2=128,
-                 seed=0, hp=None, group=False, privacy=None):
+                 seed=0, hp=None, group=False, privacy=None, whole_round=None):
         """mats: {'train': (data_csr, target_csr), 'test': (...)} global scipy CSR matrices (rows = aligned entity)."""
         self.rank, self.world, self.device = rank, world, device
         self.K = len(data_split)
@@ -67,6 +69,19 @@ class AssistRounds:
         self.n_rows = y["train"].shape[0]
         self.my_orgs = list(range(rank * self.chunk, min(self.K, (rank + 1) * self.chunk)))
         self.org_data, self.org_test_data, self.eng = {}, {}, {}
+        # One plan + one graph per organization and ROUND (instead of per local epoch) when the plan buffers fit: ~40 B
+        # per target entry and planned epoch, i.e. 0.7 GB per organization at ML1M shape with 20 epochs. Same batches,
+        # same step order, same dropout draws -> identical results; 20x fewer plan kernels and graph launches.
+        nnz_t = y["train"].nnz
+        plan_bytes = 40 * nnz_t * local_epochs * max(1, len(self.my_orgs))
+        env = os.environ.get("DMT_WHOLE_ROUND")
+        if whole_round is None:
+            whole_round = (plan_bytes < WHOLE_ROUND_PLAN_BUDGET) if env is None else env == "1"
+        # 32-bit (batch, column) sort keys and int32 entry offsets bound what one plan can cover
+        n_b = -(-self.n_rows // batch_rows) * local_epochs
+        if n_b * max(y["train"].shape[1], 1) >= 2 ** 32 or nnz_t * local_epochs >= 2 ** 31 - 2:
+            whole_round = False
+        self.whole_round = bool(whole_round) and not group
         for k in self.my_orgs:
             d = E.DeviceCSR(mats["train"][0][:, cols[k]].tocsr(), device)
             self.org_data[k] = d
@@ -74,7 +89,7 @@ class AssistRounds:
             same = mats["test"][0] is mats["train"][0]
             self.org_test_data[k] = d if same else E.DeviceCSR(mats["test"][0][:, cols[k]].tocsr(), device)
             self.eng[k] = E.OrgEngine(d, self.state.y["train"], batch_rows, H1, H2, native.LOSS_KIND[target_mode],
-                                      plan_epochs=local_epochs if group else 1)
+                                      plan_epochs=local_epochs if (group or self.whole_round) else 1)
         # optional lockstep group: one launch per step kernel for ALL organizations of this rank (dmt_group_*).
         # Measured on B200 at ML1M shape (18 organizations): 281 ms/round against 257 ms for per-organization graphs
         # on private streams — both are bound by the same L2 gather traffic — so per-organization graphs stay default.
@@ -181,6 +196,20 @@ class AssistRounds:
             n_batches = len(glob) - 1
             self.group.train([rows_dev[o] for o in self.my_orgs], offs, len(rows_dev[self.my_orgs[0]]), n_batches,
                              nts, nds, seeds, batch_loss=[loss_bufs[o] for o in self.my_orgs], **self.hp)
+            self._finish_round_local(t, loss_bufs)
+            return
+        if self.whole_round:
+            # one plan + one graph launch per organization for all local epochs of the round
+            for org in self.my_orgs:
+                lays = layouts[org]
+                base = np.cumsum([0] + [len(l.rows) for l in lays[:-1]])
+                glob = np.concatenate([l.row_off[:-1] + b for l, b in zip(lays, base)] +
+                                      [np.array([sum(len(l.rows) for l in lays)])]).astype(np.int32)
+                goff = E.to_dev(glob, self.device)
+                self.eng[org]._keep_alive.append(goff)
+                self.eng[org].h.train_epoch(rows_dev[org], goff, sum(l.n_t for l in lays), sum(l.n_d for l in lays),
+                                            keep=None, seed=E.he_seed(self.seed, org, t, 0),
+                                            epoch_loss=loss_bufs[org], **self.hp)
             self._finish_round_local(t, loss_bufs)
             return
         # per-organization graphs, epoch-major enqueue: every organization's stream gets work early, so the GPU never

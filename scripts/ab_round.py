@@ -38,6 +38,6 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n_rounds
 eng = R.eng[R.my_orgs[0]]
 prof = eng.h.profile_step(b=0, reps=20)
-print(json.dumps({"decoder": eng.decoder, "fanout": R.fanout, "group": group, "world": world, "orgs": len(R.my_orgs), "ms_per_round": ms,
+print(json.dumps({"decoder": eng.decoder, "fanout": R.fanout, "whole_round": R.whole_round, "group": group, "world": world, "orgs": len(R.my_orgs), "ms_per_round": ms,
                   "step_kernel_ms_org0": {k: round(v, 5) for k, v in prof.items()},
                   "step_sum_us": 1e3 * sum(prof.values())}))

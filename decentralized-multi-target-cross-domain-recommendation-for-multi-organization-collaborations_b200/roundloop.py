@@ -25,6 +25,10 @@ from . import native
 FANOUT_MAX_ORGS = 9
 # device memory the whole-round plans of a rank may take (bytes); DMT_WHOLE_ROUND=0|1 overrides
 WHOLE_ROUND_PLAN_BUDGET = 48 << 30
+# Measured on one B200 at ML1M shape (ms per round, per-epoch -> whole-round): 3 organizations 63.0 -> 59.9, 18
+# organizations 254.5 -> 263.0 (epoch-major enqueue of small plans keeps 18 graphs better interleaved and the plan
+# tables L2-resident), so it is used for ranks that hold few organizations.
+WHOLE_ROUND_MAX_ORGS = 5
 
 
 def xavier_uniform_(shape, device, generator=None):
@@ -76,7 +80,8 @@ class AssistRounds:
         plan_bytes = 40 * nnz_t * local_epochs * max(1, len(self.my_orgs))
         env = os.environ.get("DMT_WHOLE_ROUND")
         if whole_round is None:
-            whole_round = (plan_bytes < WHOLE_ROUND_PLAN_BUDGET) if env is None else env == "1"
+            whole_round = (plan_bytes < WHOLE_ROUND_PLAN_BUDGET and len(self.my_orgs) <= WHOLE_ROUND_MAX_ORGS) \
+                if env is None else env == "1"
         # 32-bit (batch, column) sort keys and int32 entry offsets bound what one plan can cover
         n_b = -(-self.n_rows // batch_rows) * local_epochs
         if n_b * max(y["train"].shape[1], 1) >= 2 ** 32 or nnz_t * local_epochs >= 2 ** 31 - 2:

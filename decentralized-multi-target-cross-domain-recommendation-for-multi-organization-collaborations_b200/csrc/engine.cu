@@ -12,7 +12,6 @@
 // 148 SMs even though a single 500-row batch cannot.
 #include <cub/cub.cuh>
 
-#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -77,7 +76,6 @@ struct dmt_org {
     int64_t dec_chunk_cap, dec_part_rows;
     // tensor-core decoder (decoder_tc.cu)
     int dec_mode, dec_passes;
-    int seg_sliced;  // 1: dW4/dW1 by the shared-memory-sliced segmented reduction (batch slice fits shared memory)
     int fanout;  // 1: the backward pass of a step is enqueued as parallel branches (dmt_org_set_fanout)
     float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
     // tables of per-row CSR windows at 128-column tile borders, one per target CSR seen (train targets, predict splits)
@@ -408,12 +406,8 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
         ChunkedSegs cs{o->pt.perm, o->pt.ent_row, o->pt.seg_key, o->pt.seg_off, o->pt.batch_seg_off,
                        o->pt.seg_chunk_off, o->pt.chunk_seg, o->pt.batch_chunk_off, o->pt.part, o->pt.part_bias, b,
                        o->n_dec};
-        if (o->seg_sliced) {
-            if ((rc = launch_segment_sliced(cs, o->n_dec, o->gbuf, o->a3, H1, B, o->row_off_buf, G + o->oW4,
-                                            G + o->ob4, o->active, sA)))
-                return rc;
-        } else if ((rc = launch_segment_chunks(cs, o->n_dec * 2, o->n_dec, o->gbuf, o->a3, H1, G + o->oW4, G + o->ob4,
-                                               o->active, sA)))
+        if ((rc = launch_segment_chunks(cs, o->n_dec * 2, o->n_dec, o->gbuf, o->a3, H1, G + o->oW4, G + o->ob4,
+                                        o->active, sA)))
             return rc;
     }
     // dense backward: dW3/db3 on branch B, dZ2 on the main stream, then dW2/db2 on branch C next to dZ1
@@ -431,12 +425,8 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
         ChunkedSegs cs{o->pd.perm, o->pd.ent_row, o->pd.seg_key, o->pd.seg_off, o->pd.batch_seg_off,
                        o->pd.seg_chunk_off, o->pd.chunk_seg, o->pd.batch_chunk_off, o->pd.part, o->pd.part_bias, b,
                        o->n_enc};
-        if (o->seg_sliced) {
-            if ((rc = launch_segment_sliced(cs, o->n_enc, o->dval_ord, o->dz1, H1, B, o->row_off_buf, G + o->oW1,
-                                            nullptr, o->active, st)))
-                return rc;
-        } else if ((rc = launch_segment_chunks(cs, o->n_enc * 2, o->n_enc, o->dval_ord, o->dz1, H1, G + o->oW1,
-                                               nullptr, o->active, st)))
+        if ((rc = launch_segment_chunks(cs, o->n_enc * 2, o->n_enc, o->dval_ord, o->dz1, H1, G + o->oW1, nullptr,
+                                        o->active, st)))
             return rc;
     }
     // join: the norm reads every gradient
@@ -571,10 +561,6 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     A(dalloc(&o->t_chunk_row, o->dec_chunk_cap)); A(dalloc(&o->t_batch_chunk, o->nb_cap + 2));
     A(dalloc(&o->dz_part, o->dec_part_rows * H1)); A(dalloc(&o->loss_part, o->dec_part_rows));
     o->dec_mode = 0; o->dec_passes = 3;
-    {
-        const char* env = getenv("DMT_SEG_SLICED");
-        o->seg_sliced = segment_sliced_fits(batch_rows) && !(env && env[0] == '0');
-    }
     A(dalloc(&o->tc_scratch, decoder_tc_scratch_floats(batch_rows, n_dec, H1)));
     A(dalloc(&o->gbuf, t_cap)); A(dalloc(&o->dval_ord, d_cap)); A(dalloc(&o->row_batch, o->rows_cap + 1));
     A(dalloc(&o->active, o->nb_cap + 1));

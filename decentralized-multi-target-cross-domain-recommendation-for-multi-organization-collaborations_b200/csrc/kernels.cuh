@@ -134,11 +134,6 @@ struct ChunkedSegs {
 };
 int launch_segment_chunks(ChunkedSegs cs, int n_chunk_max, int n_seg_max, const float* coef, const float* src,
                           int width, float* grad, float* bias_grad, const int32_t* active, cudaStream_t st);
-// shared-memory-sliced form: one launch, no partial rows (needs batch_rows * 256 B of shared memory per CTA)
-bool segment_sliced_fits(int batch_rows);
-int launch_segment_sliced(ChunkedSegs cs, int n_seg_max, const float* coef, const float* src, int width,
-                          int batch_rows, const int32_t* row_off, float* grad, float* bias_grad,
-                          const int32_t* active, cudaStream_t st);
 int build_seg_chunks(const int32_t* seg_off, const int32_t* n_seg, int64_t cap, int32_t* n_ch, int32_t* seg_chunk_off,
                      int32_t* chunk_seg, void* temp, int64_t temp_bytes, cudaStream_t st);
 

@@ -334,91 +334,6 @@ int launch_group_segments(const OrgDev* orgs, int G, int b, int side, int n_cols
     return 0;
 }
 
-// ---------------------------------------------------------------- shared-memory-sliced form (engine)
-// grad[col, slice] = sum over the (batch, col) segment of coef * src[row, slice] with a 64-wide column slice of the
-// batch's source matrix (A3 or dZ1: <= batch_rows x 64 fp32 = 128 KB at 500 rows) staged ONCE per CTA in shared
-// memory: the per-entry 1 KB row gathers of the chunked form (71 MB of L1/L2 traffic per ML1M step) become 256 B
-// shared-memory reads, every segment is summed whole by one half-warp in plan order (no partial rows, no finish
-// kernel, bit-reproducible), and bias_grad falls out of the same walk. Grid: x = segment groups, y = H / 64 slices.
-constexpr int kSlice = 64;
-
-__global__ void __launch_bounds__(256) segment_sliced_kernel(ChunkedSegs cs, const float* __restrict__ coef,
-                                                             const float* __restrict__ src, int W, int n_rows_cap,
-                                                             const int32_t* __restrict__ row_off,
-                                                             float* __restrict__ grad, float* __restrict__ bias_grad,
-                                                             const int32_t* __restrict__ active) {
-    extern __shared__ float s_src[];  // [rows of the batch][kSlice]
-    if (active != nullptr && active[cs.b] == 0) return;
-    const int M = min(n_rows_cap, row_off[cs.b + 1] - row_off[cs.b]);
-    const int slice = blockIdx.y * kSlice;
-    // stage the slice: 16 lanes x float4 = one 256 B row segment per half-warp
-    for (int i = threadIdx.x; i < M * (kSlice / 4); i += blockDim.x) {
-        const int r = i >> 4, c4 = i & 15;
-        reinterpret_cast<float4*>(s_src)[i] = ld4(src + (int64_t)r * W + slice + c4 * 4);
-    }
-    __syncthreads();
-    const int hl = threadIdx.x & 15;                       // lane inside the half-warp
-    const unsigned hmask = 0xffffu << (threadIdx.x & 16);  // this half-warp's lanes
-    const int hw = blockIdx.x * 16 + (threadIdx.x >> 4), n_hw = gridDim.x * 16;
-    const int s_lo = cs.batch_seg_off[cs.b], s_hi = cs.batch_seg_off[cs.b + 1];
-    const uint32_t key_base = (uint32_t)cs.b * (uint32_t)cs.n_cols;
-    for (int s = s_lo + hw; s < s_hi; s += n_hw) {
-        const int e0 = cs.seg_off[s], e1 = cs.seg_off[s + 1];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float bsum = 0.f;
-        for (int eb = e0; eb < e1; eb += 16) {
-            float c_l = 0.f;
-            int r_l = 0;
-            if (eb + hl < e1) {
-                const int id = cs.perm[eb + hl];
-                c_l = coef[id];
-                r_l = cs.ent_row[id];
-            }
-            const int cnt = min(16, e1 - eb);
-            for (int i = 0; i < cnt; ++i) {
-                const float c = __shfl_sync(hmask, c_l, i, 16);
-                const int r = __shfl_sync(hmask, r_l, i, 16);
-                const float4 x = reinterpret_cast<const float4*>(s_src)[r * (kSlice / 4) + hl];
-                acc.x = fmaf(c, x.x, acc.x);
-                acc.y = fmaf(c, x.y, acc.y);
-                acc.z = fmaf(c, x.z, acc.z);
-                acc.w = fmaf(c, x.w, acc.w);
-                bsum += c;
-            }
-        }
-        const int row_out = (int)((uint32_t)cs.seg_key[s] - key_base);
-        st4(grad + (int64_t)row_out * W + slice + hl * 4, acc);
-        if (bias_grad != nullptr && blockIdx.y == 0 && hl == 0) bias_grad[row_out] = bsum;
-    }
-}
-
-bool segment_sliced_fits(int batch_rows) { return (size_t)batch_rows * kSlice * 4 <= 200 * 1024; }
-
-int launch_segment_sliced(ChunkedSegs cs, int n_seg_max, const float* coef, const float* src, int width,
-                          int batch_rows, const int32_t* row_off, float* grad, float* bias_grad,
-                          const int32_t* active, cudaStream_t st) {
-    if (width % kSlice != 0 || !segment_sliced_fits(batch_rows)) {
-        set_error("segment_sliced: width must be a multiple of 64 and the batch slice must fit shared memory");
-        return DMT_E_ARG;
-    }
-    const int smem = batch_rows * kSlice * 4;
-    static int configured = 0;
-    if (configured < smem) {
-        DMT_CUDA(cudaFuncSetAttribute(segment_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
-    const int slices = width / kSlice;
-    // one CTA per SM across the slices; at least ~4 segments per half-warp so the staging of the slice is amortised
-    int gx = kNumSMs / slices;
-    const int want = (n_seg_max + 63) / 64;
-    if (gx > want) gx = want;
-    if (gx < 1) gx = 1;
-    segment_sliced_kernel<<<dim3(gx, slices), 256, smem, st>>>(cs, coef, src, width, batch_rows, row_off, grad,
-                                                               bias_grad, active);
-    DMT_LAUNCH_CHECK();
-    return 0;
-}
-
 int launch_segment_chunks(ChunkedSegs cs, int n_chunk_max, int n_seg_max, const float* coef, const float* src,
                           int width, float* grad, float* bias_grad, const int32_t* active, cudaStream_t st) {
     int blocks = (n_chunk_max + 7) / 8;

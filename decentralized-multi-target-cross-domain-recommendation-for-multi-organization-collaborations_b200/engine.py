@@ -306,6 +306,7 @@ class MtalState:
         self.O = {k: self.O_full[k][:self.K] for k in y}
         self._views = {}
         self._eval_meta = {}
+        self._combine_cache = None
 
     def residual(self, F, split, clamp, out=None):
         return native.residual(F, self.y[split].data, self.loss_kind, 1.0 if clamp else 0.0, out)
@@ -419,8 +420,12 @@ class MtalState:
         for i, (rate, weight) in enumerate(fitted):
             rate_col[self.data_split[i]] = rate.numpy()
             S[i] = torch.softmax(weight, -1).numpy()
-        rate_col_d = to_dev(rate_col, self.device)
-        S_d = to_dev(S, self.device)
+        # constant rates / weights repeat every round: upload once (a pageable copy on the compute stream would make the
+        # host wait for the whole round that the stream is still ordered behind)
+        ck = (rate_col.tobytes(), S.tobytes())
+        if self._combine_cache is None or self._combine_cache[0] != ck:
+            self._combine_cache = (ck, to_dev(rate_col, self.device), to_dev(S, self.device))
+        rate_col_d, S_d = self._combine_cache[1], self._combine_cache[2]
         F_next = {}
         for k in self.splits:
             me = self.match_end(k, match_rate) if match_rate < 1 else None

@@ -113,6 +113,9 @@ class AssistRounds:
         self.host_gen = torch.Generator()
         self.host_gen.manual_seed(seed * 7919 + rank)
         self.round_losses = {}
+        self._up_stream = None
+        self._pending_uploads = []
+        self._held_uploads = []
 
     # ------------------------------------------------------------------ round 0 (replicated: cheap)
     def round0(self):
@@ -168,32 +171,58 @@ class AssistRounds:
             if self.privacy is not None:  # src/assist.py:59-60; same noise on every rank (seeded by round and split)
                 st.privatize(self.residual[k], self.privacy[0], self.privacy[1], E.he_seed(self.seed, t, i, 1 << 22))
         loss_bufs = {}
-        layouts, rows_dev, off_dev = {}, {}, {}
+        layouts, rows_dev, off_dev, glob_dev = {}, {}, {}, {}
+        # (1) host-only preparation of every organization's epochs: no CUDA call, so it overlaps the previous round that
+        #     the GPU is still executing (run_round never synchronises)
+        host = {}
+        need_glob = self.whole_round or self.group is not None
         for org in self.my_orgs:
             eng = self.eng[org]
-            self.gen.manual_seed(E.he_seed(self.seed, org, t, 1 << 20) & (2 ** 63 - 1))
             self.host_gen.manual_seed(E.he_seed(self.seed, org, t, 1 << 21) & (2 ** 63 - 1))
-            flat0 = init_flat_params(eng.n_enc, eng.n_dec, self.H1, self.H2, self.device, self.gen)
-            eng.set_round(flat0, self.residual["train"])
             lays = [E.FastEpochLayout(torch.randperm(self.n_rows, generator=self.host_gen).numpy(), self.batch_rows,
                                       eng.d_len, eng.t_len) for _ in range(self.local_epochs)]
             layouts[org] = lays
-            rows_dev[org] = E.to_dev(np.concatenate([l.rows for l in lays]).astype(np.int32), self.device)
-            off_dev[org] = E.to_dev(np.concatenate([l.row_off for l in lays]), self.device)
-            loss_bufs[org] = torch.zeros(sum(len(l.active) for l in lays), device=self.device)
+            rows_np = np.concatenate([l.rows for l in lays]).astype(np.int32)
+            off_np = np.concatenate([l.row_off for l in lays]).astype(np.int32)
+            glob_np = None
+            if need_glob:
+                base = np.cumsum([0] + [len(l.rows) for l in lays[:-1]])
+                glob_np = np.concatenate([l.row_off[:-1] + b for l, b in zip(lays, base)] +
+                                         [np.array([sum(len(l.rows) for l in lays)])]).astype(np.int32)
+            host[org] = (rows_np, off_np, glob_np)
+        # (2) uploads from pinned staging on a side stream: not ordered behind the compute streams, so neither the
+        #     copies nor the host wait for the previous round to drain
+        self._reap_uploads()
+        up = self._upload_stream()
+        held = []
+        with torch.cuda.stream(up):
+            for org in self.my_orgs:
+                rows_np, off_np, glob_np = host[org]
+                rows_dev[org] = self._upload(rows_np)
+                off_dev[org] = self._upload(off_np)
+                held += [rows_dev[org], off_dev[org]]
+                if glob_np is not None:
+                    glob_dev[org] = self._upload(glob_np)
+                    held.append(glob_dev[org])
+        uploaded = up.record_event()
+        torch.cuda.current_stream().wait_event(uploaded)
+        # (3) device side: fresh parameters, targets, loss buffers
+        for org in self.my_orgs:
+            eng = self.eng[org]
+            self.gen.manual_seed(E.he_seed(self.seed, org, t, 1 << 20) & (2 ** 63 - 1))
+            flat0 = init_flat_params(eng.n_enc, eng.n_dec, self.H1, self.H2, self.device, self.gen)
+            eng.set_round(flat0, self.residual["train"])
+            loss_bufs[org] = torch.zeros(sum(len(l.active) for l in layouts[org]), device=self.device)
             eng.h.wait_current()
-            eng._keep_alive += [rows_dev[org], off_dev[org], loss_bufs[org]]
+            eng._keep_alive += [loss_bufs[org]]
+        self._held_uploads = held
         same_rows = len({len(rows_dev[o]) for o in self.my_orgs}) == 1
         if self.group is not None and same_rows:
             # whole round of every organization: one plan per organization + ONE graph launch for all steps
             offs, nts, nds, seeds = [], [], [], []
             for org in self.my_orgs:
                 lays = layouts[org]
-                base = np.cumsum([0] + [len(l.rows) for l in lays[:-1]])
-                glob = np.concatenate([l.row_off[:-1] + b for l, b in zip(lays, base)] +
-                                      [np.array([sum(len(l.rows) for l in lays)])]).astype(np.int32)
-                off_dev[org] = E.to_dev(glob, self.device)
-                self.eng[org]._keep_alive.append(off_dev[org])
+                off_dev[org] = glob_dev[org]
                 offs.append(off_dev[org])
                 nts.append(sum(l.n_t for l in lays))
                 nds.append(sum(l.n_d for l in lays))
@@ -207,11 +236,7 @@ class AssistRounds:
             # one plan + one graph launch per organization for all local epochs of the round
             for org in self.my_orgs:
                 lays = layouts[org]
-                base = np.cumsum([0] + [len(l.rows) for l in lays[:-1]])
-                glob = np.concatenate([l.row_off[:-1] + b for l, b in zip(lays, base)] +
-                                      [np.array([sum(len(l.rows) for l in lays)])]).astype(np.int32)
-                goff = E.to_dev(glob, self.device)
-                self.eng[org]._keep_alive.append(goff)
+                goff = glob_dev[org]
                 self.eng[org].h.train_epoch(rows_dev[org], goff, sum(l.n_t for l in lays), sum(l.n_d for l in lays),
                                             keep=None, seed=E.he_seed(self.seed, org, t, 0),
                                             epoch_loss=loss_bufs[org], **self.hp)
@@ -244,6 +269,26 @@ class AssistRounds:
         for org in self.my_orgs:
             self.eng[org].h.signal_current()  # the current stream waits for every organization's stream
         self.round_losses[t] = loss_bufs
+        # the uploaded row lists live on the side stream's pool: keep them referenced until this round has run
+        self._pending_uploads.append((torch.cuda.current_stream().record_event(), self._held_uploads))
+        self._held_uploads = []
+
+    def _upload_stream(self):
+        if self._up_stream is None:
+            self._up_stream = torch.cuda.Stream(device=self.device)
+        return self._up_stream
+
+    def _upload(self, arr):
+        """numpy -> pinned staging (torch's caching host allocator: same sizes every round, so no cudaHostAlloc after
+        the first rounds) -> device, asynchronously on the current (upload) stream."""
+        t = torch.from_numpy(arr)
+        E.XFER["h2d"] += t.numel() * t.element_size()
+        pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        pin.copy_(t)
+        return pin.to(self.device, non_blocking=True)
+
+    def _reap_uploads(self):
+        self._pending_uploads = [(ev, ts) for ev, ts in self._pending_uploads if not ev.query()]
 
     def combine(self):
         """Replicated part: Assist.update over the exchanged outputs -> F_t on every rank."""

@@ -227,7 +227,7 @@ class AssistRounds:
                 nts.append(sum(l.n_t for l in lays))
                 nds.append(sum(l.n_d for l in lays))
                 seeds.append(E.he_seed(self.seed, org, t, 0))
-            n_batches = len(glob) - 1
+            n_batches = len(host[self.my_orgs[0]][2]) - 1
             self.group.train([rows_dev[o] for o in self.my_orgs], offs, len(rows_dev[self.my_orgs[0]]), n_batches,
                              nts, nds, seeds, batch_loss=[loss_bufs[o] for o in self.my_orgs], **self.hp)
             self._finish_round_local(t, loss_bufs)

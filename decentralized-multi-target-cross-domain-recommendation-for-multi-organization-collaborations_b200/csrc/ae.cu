@@ -224,19 +224,20 @@ __device__ __forceinline__ void ae_decoder_chunk_body(const int32_t* __restrict_
                                                               const int32_t* __restrict__ n_targets,
                                                               const int32_t* __restrict__ ent_off, DecChunks dc,
                                                               float* __restrict__ gout, BatchRef br) {
-    // One WARP per chunk of <= kDecChunk targets of one batch row; warps never synchronise with each other (no shared
-    // memory, no block barrier), so the eight warps of a block sit in different phases of their chunks and the weight
-    // rows of one overlap the index loads of another. Inside a chunk the targets are walked in groups of four 1 KB
-    // weight rows, software-pipelined: group g+1 is in flight while group g is reduced (eight rows outstanding per
-    // warp). The warp's accumulator IS the chunk's partial dZ3 row and is written straight from registers.
     constexpr int H = VEC * 128;
+    constexpr int PER_WARP = kDecChunk / 8;  // 16 targets per warp
+    constexpr int GROUPS = PER_WARP / 4;     // in groups of four 1 KB weight rows
+    // double-buffered so that a chunk needs ONE block barrier: the next chunk's partials go to the other buffer, and
+    // nobody can be two chunks ahead of a thread that still reads (it would have to pass the barrier in between)
+    __shared__ float s_acc[2][8][H];
+    __shared__ float s_loss[2][8];
     int lo, hi;
     if (!batch_range(br, lo, hi)) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c_lo = dc.batch_chunk_off[br.b], c_hi = dc.batch_chunk_off[br.b + 1];
     const float inv_n = 1.f / (float)n_targets[br.b];
-    const int warp = blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = gridDim.x * 8;
-    for (int c = c_lo + warp; c < c_hi; c += n_warps) {
+    int buf = 0;
+    for (int c = c_lo + blockIdx.x; c < c_hi; c += gridDim.x, buf ^= 1) {
         const int j = dc.chunk_row[c];  // epoch-wide batch-row index
         const int u = rows[j];
         const int k = c - dc.chunk_off[j];
@@ -252,71 +253,86 @@ __device__ __forceinline__ void ae_decoder_chunk_body(const int32_t* __restrict_
             acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float loss_acc = 0.f;
-        for (int eb = e0; eb < e1; eb += 32) {  // 32 targets per pass: columns / targets loaded coalesced
-            const int cnt = min(32, e1 - eb);
-            int c_l = 0;
-            float y_l = 0.f;
-            if (lane < cnt) {
-                c_l = indices[eb + lane];
-                y_l = target[eb + lane];
-            }
-            float o_l = 0.f;
-            const int n_groups = (cnt + 3) >> 2;
+        const int eb = e0 + wid * PER_WARP;
+        const int cnt = max(0, min(PER_WARP, e1 - eb));
+        int c_l = 0;
+        float y_l = 0.f;
+        if (lane < cnt) {
+            c_l = indices[eb + lane];
+            y_l = target[eb + lane];
+        }
+        float o_l = 0.f;
+        if (cnt > 0) {
+            // software pipeline: the four weight rows of group g+1 are in flight while group g is reduced, so eight 1 KB
+            // rows per warp are outstanding instead of a load-wait-compute sequence per group. Slots past `cnt` re-read
+            // the last valid row and contribute with g = 0.
             float4 w[2][4][VEC];
             float bb[2][4];
-            // slots past `cnt` re-read the last valid row and contribute with g = 0
-#define DMT_LOAD_GROUP(g, slot)                                                                            \
-    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                        \
-        const int col = __shfl_sync(0xffffffffu, c_l, min(4 * (g) + q, cnt - 1));                          \
-        _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                    \
-            w[slot][q][v] = ld4(W4 + (int64_t)col * H + v * 128 + lane * 4);                               \
-        bb[slot][q] = b4[col];                                                                             \
-    }
-#define DMT_REDUCE_GROUP(g, slot)                                                                          \
-    {                                                                                                      \
-        float d[4];                                                                                        \
-        _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                    \
-            d[q] = 0.f;                                                                                    \
-            _Pragma("unroll") for (int v = 0; v < VEC; ++v)                                                \
-                d[q] += a[v].x * w[slot][q][v].x + a[v].y * w[slot][q][v].y + a[v].z * w[slot][q][v].z +   \
-                        a[v].w * w[slot][q][v].w;                                                          \
-        }                                                                                                  \
-        _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                                    \
-            const int t = 4 * (g) + q;                                                                     \
-            const bool valid = t < cnt;                                                                    \
-            d[q] = warp_sum(d[q]) + bb[slot][q];                                                           \
-            if (lane == t && valid) o_l = d[q];                                                            \
-            const float y = __shfl_sync(0xffffffffu, y_l, min(t, cnt - 1));                                \
-            const float gq = valid ? loss_grad(loss_kind, d[q], y) * inv_n : 0.f;                          \
-            _Pragma("unroll") for (int v = 0; v < VEC; ++v) {                                              \
-                acc[v].x = fmaf(gq, w[slot][q][v].x, acc[v].x);                                            \
-                acc[v].y = fmaf(gq, w[slot][q][v].y, acc[v].y);                                            \
-                acc[v].z = fmaf(gq, w[slot][q][v].z, acc[v].z);                                            \
-                acc[v].w = fmaf(gq, w[slot][q][v].w, acc[v].w);                                            \
-            }                                                                                              \
-        }                                                                                                  \
-    }
-            DMT_LOAD_GROUP(0, 0)
-            for (int g = 0; g < n_groups; g += 2) {  // two groups per trip: the buffer index stays a compile-time constant
-                if (g + 1 < n_groups) DMT_LOAD_GROUP(g + 1, 1)
-                DMT_REDUCE_GROUP(g, 0)
-                if (g + 1 < n_groups) {
-                    if (g + 2 < n_groups) DMT_LOAD_GROUP(g + 2, 0)
-                    DMT_REDUCE_GROUP(g + 1, 1)
+            auto load_group = [&](int g, int slot) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = __shfl_sync(0xffffffffu, c_l, min(4 * g + q, cnt - 1));
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) w[slot][q][v] = ld4(W4 + (int64_t)col * H + v * 128 + lane * 4);
+                    bb[slot][q] = b4[col];
+                }
+            };
+            load_group(0, 0);
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                if (4 * g < cnt) {  // warp-uniform
+                    const int slot = g & 1;
+                    if (g + 1 < GROUPS && 4 * (g + 1) < cnt) load_group(g + 1, (g + 1) & 1);
+                    float d[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        d[q] = 0.f;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+                            d[q] += a[v].x * w[slot][q][v].x + a[v].y * w[slot][q][v].y + a[v].z * w[slot][q][v].z +
+                                    a[v].w * w[slot][q][v].w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int t = 4 * g + q;
+                        const bool valid = t < cnt;
+                        d[q] = warp_sum(d[q]) + bb[slot][q];
+                        if (lane == t && valid) o_l = d[q];
+                        const float y = __shfl_sync(0xffffffffu, y_l, min(t, cnt - 1));
+                        const float gq = valid ? loss_grad(loss_kind, d[q], y) * inv_n : 0.f;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            acc[v].x = fmaf(gq, w[slot][q][v].x, acc[v].x);
+                            acc[v].y = fmaf(gq, w[slot][q][v].y, acc[v].y);
+                            acc[v].z = fmaf(gq, w[slot][q][v].z, acc[v].z);
+                            acc[v].w = fmaf(gq, w[slot][q][v].w, acc[v].w);
+                        }
+                    }
                 }
             }
-#undef DMT_LOAD_GROUP
-#undef DMT_REDUCE_GROUP
-            if (lane < cnt) {
-                gout[out_base + eb + lane] = loss_grad(loss_kind, o_l, y_l) * inv_n;
-                loss_acc += loss_value(loss_kind, o_l, y_l);
-            }
         }
-        const int64_t slot_out = c - c_lo;
+        if (lane < cnt) {
+            gout[out_base + eb + lane] = loss_grad(loss_kind, o_l, y_l) * inv_n;
+            loss_acc = loss_value(loss_kind, o_l, y_l);
+        }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) st4(dc.dz_part + slot_out * H + v * 128 + lane * 4, acc[v]);
+        for (int v = 0; v < VEC; ++v) st4(&s_acc[buf][wid][v * 128 + lane * 4], acc[v]);
         loss_acc = warp_sum(loss_acc);
-        if (lane == 0) dc.loss_part[slot_out] = loss_acc;
+        if (lane == 0) s_loss[buf][wid] = loss_acc;
+        __syncthreads();
+        const int64_t slot_out = c - c_lo;
+        for (int h = threadIdx.x; h < H; h += 256) {
+            float s = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) s += s_acc[buf][w8][h];
+            dc.dz_part[slot_out * H + h] = s;
+        }
+        if (threadIdx.x == 0) {
+            float l = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) l += s_loss[buf][w8];
+            dc.loss_part[slot_out] = l;
+        }
     }
 }
 
@@ -394,11 +410,9 @@ int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const i
                              const int32_t* n_targets, const int32_t* ent_off, DecChunks dc, float* gout, float* dZ3,
                              float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st) {
     if (n_rows_max <= 0) return 0;
-    // one warp per chunk, persistent over the batch's chunks (their count is known only on the device): enough blocks
-    // for every chunk of a full batch up to two per SM; the other organizations' graphs fill the rest of the machine
-    int blocks = (int)(((int64_t)n_rows_max * 2 + 7) / 8);  // ~2 chunks per row on average is already generous
-    if (blocks > kNumSMs * 2) blocks = kNumSMs * 2;
-    if (blocks < 1) blocks = 1;
+    // persistent over the batch's chunks (count known only on the device); 2 blocks per SM leaves room for the other
+    // organizations' graphs that run concurrently on their own streams
+    const int blocks = kNumSMs * 2;
 #define DMT_DECC(V)                                                                                             \
     ae_decoder_chunk_kernel<V><<<blocks, 256, 0, st>>>(rows, indptr, indices, target, A3, W4, b4, loss_kind,   \
                                                        n_targets, ent_off, dc, gout, br)

@@ -21,14 +21,15 @@ from . import native
 
 # organizations per GPU up to which a step's backward pass is enqueued as parallel graph branches (dmt_org_set_fanout);
 # DMT_FANOUT=0|1 overrides. Measured on one B200 at ML1M shape, ms per round without -> with: 3 organizations 72.9 -> 63.3,
-# 5: 96.1 -> 85.5, 9: 140.4 -> 130.7, 18: 271 -> 301 (their graphs already fill the machine).
+# 5: 96.1 -> 85.5, 9: 140.4 -> 130.7; at 18 the round is throughput-bound and the shape of the step does not matter
+# (214.7 vs 215.0 once the host no longer stalls behind the compute streams).
 FANOUT_MAX_ORGS = 9
 # device memory the whole-round plans of a rank may take (bytes); DMT_WHOLE_ROUND=0|1 overrides
 WHOLE_ROUND_PLAN_BUDGET = 48 << 30
-# Measured on one B200 at ML1M shape (ms per round, per-epoch -> whole-round): 3 organizations 63.0 -> 59.9, 18
-# organizations 254.5 -> 263.0 (epoch-major enqueue of small plans keeps 18 graphs better interleaved and the plan
-# tables L2-resident), so it is used for ranks that hold few organizations.
-WHOLE_ROUND_MAX_ORGS = 5
+# Measured on one B200 at ML1M shape (ms per round, per-epoch -> whole-round): 3 organizations 63.0 -> 59.9, 9
+# organizations 111.2 -> 108.6, 18 organizations 214.7 -> 214.0 (throughput-bound: no difference), so it is used for
+# ranks that hold few organizations, where the per-organization chain of dependent steps is what bounds a round.
+WHOLE_ROUND_MAX_ORGS = 9
 
 
 def xavier_uniform_(shape, device, generator=None):

@@ -111,6 +111,7 @@ class Assist:
         if 'cs' in cfg:
             raise NotImplementedError("cold-start ('cs') runs are out of scope (DESIGN.md)")
         st = self._mtal()
+        import organization as _org_mod
         for k in organization_outputs[0]:
             for j, out in enumerate(organization_outputs):
                 m = out[k]
@@ -120,6 +121,9 @@ class Assist:
                 if dev_vals is None:
                     dev_vals = E.to_dev(np.asarray(m.data, dtype=np.float32), st.device)
                 st.O[k][j].copy_(dev_vals)
+        # the round's barrier: everything the organizations deferred (train-loss log lines) is written now, before
+        # the driver evaluates and resets its logger
+        _org_mod.flush_pending()
         a = cfg['assist']
         match_rate = a['match_rate'] if 'match_rate' in a else 1.0
         F_prev = {k: self._F(iter - 1, k) for k in organization_outputs[0]}

@@ -7,6 +7,7 @@ Inputs are the reference's dataset objects (``.data`` / ``.target`` scipy CSR in
 reused across calls, keyed by the content of the CSR structure.
 """
 import sys
+import weakref
 
 import numpy as np
 import torch
@@ -59,6 +60,16 @@ def device_csr(m, with_values=True):
     return hit
 
 
+_D2H_STREAMS = {}
+
+
+def _d2h_stream(dev):
+    st = _D2H_STREAMS.get(dev)
+    if st is None:
+        st = _D2H_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def _device():
     dev = str(cfg['device'])
     if not dev.startswith('cuda'):
@@ -81,12 +92,59 @@ def _shape_target():
     raise ValueError('Not valid data mode')
 
 
+# Work the drop-in defers so that the host never waits inside the per-organization API calls of a round: train-loss
+# logging callbacks and the host copies of predictions. `flush_pending()` runs at the next natural barrier
+# (Assist.update, which needs every organization's output anyway) or when somebody actually reads the data.
+_PENDING = []
+
+
+def flush_pending():
+    global _PENDING
+    todo, _PENDING = _PENDING, []
+    for cb in todo:
+        cb()
+
+
+class LazyCSR(csr_matrix):
+    """scipy CSR whose ``data`` is still in flight from the device: the device->host copy into a pinned buffer is
+    enqueued behind the organization's work, and the values are moved into this matrix' own (fresh, pageable) array the
+    first time ``data`` is read. The reference's driver hands predict() outputs straight to Assist.update, which takes
+    the device-resident copy (``_dmt_pred_dev``) — in that flow the host copy is never waited for."""
+
+    @property
+    def data(self):
+        f = self.__dict__.get('_dmt_force')
+        if f is not None:
+            self.__dict__['_dmt_force'] = None
+            f()
+        return self.__dict__['_dmt_data']
+
+    @data.setter
+    def data(self, v):
+        self.__dict__['_dmt_data'] = v
+
+    def __reduce__(self):  # pickles / deep-copies as a plain CSR
+        return (csr_matrix, ((self.data, self.indices, self.indptr), self.shape))
+
+
 class LazyStateDict(dict):
     """state_dict whose tensors are still on the organization's stream; materialised on first read."""
 
     def __init__(self, flat, eng, n_enc, n_dec, H1, H2, on_ready=None):
         super().__init__()
         self._pending = (flat, eng, n_enc, n_dec, H1, H2, on_ready)
+        self._on_ready = on_ready
+        self._eng = eng
+
+    def _log(self):
+        """Run the train-loss logging callback once (needs the organization's training to have finished)."""
+        cb = self.__dict__.get('_on_ready')
+        if cb is not None:
+            self.__dict__['_on_ready'] = None
+            eng = self.__dict__.get('_eng')
+            if eng is not None:
+                eng.h.sync()  # the losses are written on the organization's stream
+            cb()
 
     def _force(self):
         p = self.__dict__.get('_pending')
@@ -96,8 +154,7 @@ class LazyStateDict(dict):
             eng.sync()
             sd = E.state_dict_from_flat(flat, n_enc, n_dec, H1, H2)
             dict.update(self, {k: E.to_host(v) for k, v in sd.items()})
-            if on_ready is not None:
-                on_ready()
+            self._log()
         return self
 
     def flat_device(self):
@@ -284,6 +341,8 @@ class Organization:
         self.model_state_dict[iter] = sd
         if 'dmt_sync' in cfg and cfg['dmt_sync']:
             sd._force()
+        else:
+            _PENDING.append(sd._log)  # train-loss log lines: written at the round's barrier (Assist.update)
         return
 
     # ------------------------------------------------------------------ prediction
@@ -308,11 +367,44 @@ class Organization:
             self._eng_params_iter = iter
         out = torch.empty(t.nnz, device=dev)
         eng.predict(eng_data, t, out)
-        eng.h.signal_current()
-        pred = E.to_host(out).numpy()
-        if isinstance(sd, LazyStateDict):
-            sd._force()
-        m = csr_matrix((pred, t.indices_host.astype(np.int32, copy=False), t.indptr_host.astype(np.int32, copy=False)),
-                       shape=_shape_target(), copy=False)
+        if 'dmt_sync' in cfg and cfg['dmt_sync']:
+            eng.h.signal_current()
+            pred = E.to_host(out).numpy()
+            if isinstance(sd, LazyStateDict):
+                sd._force()
+            m = csr_matrix((pred, t.indices_host.astype(np.int32, copy=False),
+                            t.indptr_host.astype(np.int32, copy=False)), shape=_shape_target(), copy=False)
+            m._dmt_pred_dev = out
+            return m
+        # device->host copy behind the organization's stream, on a side stream, into this organization's persistent
+        # pinned buffer for the split; nobody waits here
+        key = (t.nnz, id(t))
+        pins = self.__dict__.setdefault('_pred_pins', {})
+        slot = pins.get(key)
+        if slot is None:
+            slot = pins[key] = {'pin': torch.empty(t.nnz, dtype=torch.float32, pin_memory=True), 'last': None}
+        prev = slot['last']() if slot['last'] is not None else None
+        if prev is not None:
+            prev.data  # an earlier, still unread output shares the pinned buffer: give it its values first
+        eng.h.signal_current()  # Assist.update reads `out` on the current stream: order it behind this organization
+        d2h = _d2h_stream(dev)
+        with torch.cuda.stream(d2h):
+            eng.h.signal_current()  # the side stream waits for this organization's stream
+            slot['pin'].copy_(out, non_blocking=True)
+            done = d2h.record_event()
+        out.record_stream(d2h)
+        E.XFER["d2h"] += out.numel() * out.element_size()
+        host = np.empty(t.nnz, dtype=np.float32)
+        m = LazyCSR((host, t.indices_host.astype(np.int32, copy=False), t.indptr_host.astype(np.int32, copy=False)),
+                    shape=_shape_target(), copy=False)
+        pin = slot['pin']
+        dest = m.__dict__['_dmt_data']  # the array scipy actually kept
+
+        def force():
+            done.synchronize()
+            np.copyto(dest, pin.numpy())
+
+        m.__dict__['_dmt_force'] = force
+        slot['last'] = weakref.ref(m)
         m._dmt_pred_dev = out
         return m

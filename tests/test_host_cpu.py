@@ -178,3 +178,37 @@ def test_distribute_slices_the_split_entity():
         assert torch.equal(m.item_bias.weight, joint.item_bias.weight[s])
         assert torch.equal(m.user_weight.weight, joint.user_weight.weight)
         assert torch.equal(m.bias, joint.bias)
+
+
+def test_lazy_csr_and_pending_flush():
+    """Drop-in predict() outputs are scipy CSRs whose values arrive lazily; deferred log callbacks run at flush."""
+    import pickle
+
+    import numpy as np
+    from scipy.sparse import csr_matrix
+
+    import dmtcdr_b200
+
+    _, org_mod, _ = dmtcdr_b200.use_dropin()
+    m = org_mod.LazyCSR((np.empty(4, np.float32), np.array([0, 1, 0, 2], np.int32), np.array([0, 2, 4], np.int32)),
+                        shape=(2, 3), copy=False)
+    dest = m.__dict__['_dmt_data']
+    calls = []
+
+    def force():
+        calls.append(1)
+        np.copyto(dest, np.array([1, 2, 3, 4], np.float32))
+
+    m.__dict__['_dmt_force'] = force
+    assert m.nnz == 4 and m.shape == (2, 3) and not calls        # structure queries do not wait for the values
+    assert isinstance(m, csr_matrix)
+    assert m.toarray().tolist() == [[1.0, 2.0, 0.0], [3.0, 0.0, 4.0]] and calls == [1]
+    assert m.data.tolist() == [1.0, 2.0, 3.0, 4.0] and calls == [1]  # forced once
+    p = pickle.loads(pickle.dumps(m))
+    assert type(p) is csr_matrix and p.data.tolist() == [1.0, 2.0, 3.0, 4.0]
+    seen = []
+    org_mod._PENDING.append(lambda: seen.append('a'))
+    org_mod._PENDING.append(lambda: seen.append('b'))
+    org_mod.flush_pending()
+    org_mod.flush_pending()
+    assert seen == ['a', 'b']

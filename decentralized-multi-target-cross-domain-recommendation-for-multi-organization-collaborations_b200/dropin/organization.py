@@ -269,11 +269,18 @@ class Organization:
         enc, dec = cfg['ae']['encoder_hidden_size'], cfg['ae']['decoder_hidden_size']
         if len(enc) != 2 or len(dec) != 2 or enc[0] != dec[1] or enc[1] != dec[0]:
             raise NotImplementedError('the engine supports the reference AE shape [H1,H2]/[H2,H1] (src/utils.py:166-171)')
-        key = (id(d), id(t), bs)
+        # device-drawn dropout: the whole round is one plan and one graph launch when its plan buffers (~40 B per target
+        # entry and epoch) stay small — 20x fewer host calls per organization, so the last organization starts early
+        n_ep = int(cfg['local']['num_epochs'])
+        whole = (_rng_mode() != 'reference' and 40 * t.nnz * n_ep <= (2 << 30) and t.nnz * n_ep < 2 ** 31 - 2
+                 and (-(-d.shape[0] // bs) + 1) * n_ep * max(t.shape[1], d.shape[1]) < 2 ** 32)
+        plan_epochs = n_ep if whole else 1
+        key = (id(d), id(t), bs, plan_epochs)
         if getattr(self, '_eng_key', None) != key:
             if getattr(self, '_eng', None) is not None:
                 self._eng.close()
-            self._eng = E.OrgEngine(d, t, bs, enc[0], enc[1], native.LOSS_KIND[cfg['target_mode']])
+            self._eng = E.OrgEngine(d, t, bs, enc[0], enc[1], native.LOSS_KIND[cfg['target_mode']],
+                                    plan_epochs=plan_epochs)
             self._eng_key = key
             self._residual_buf = torch.empty(t.nnz, device=_device())
         return self._eng, d, t
@@ -319,6 +326,12 @@ class Organization:
                 layouts.append(lay)
                 losses.append(lo)
             loss_all = torch.cat(losses)
+        elif eng.plan_epochs >= n_epochs > 1:
+            perms = np.concatenate([torch.randperm(d.shape[0]).numpy() for _ in range(n_epochs)])
+            lay = E.FastEpochLayout(perms, bs, eng.d_len, eng.t_len, epoch_len=d.shape[0])
+            layouts.append(lay)
+            loss_all = torch.zeros(len(lay.active), device=dev)
+            eng.enqueue_round(lay, E.he_seed(cfg['seed'], self.organization_id, iter, 0), hp=hp, loss_out=loss_all)
         else:
             for _ in range(n_epochs):
                 layouts.append(E.FastEpochLayout(torch.randperm(d.shape[0]).numpy(), bs, eng.d_len, eng.t_len))

@@ -169,14 +169,22 @@ class FastEpochLayout:
     permutation slice itself — no per-batch sort on the host. Rows with neither data nor targets are still dropped
     and batches without data entries still skipped (src/models/ae.py:101, src/organization.py:153-155)."""
 
-    def __init__(self, perm, batch_size, d_len, t_len):
+    def __init__(self, perm, batch_size, d_len, t_len, epoch_len=None):
+        """epoch_len: ``perm`` is the concatenation of several epochs' permutations of that length (a whole round in one
+        layout: batch ids keep counting across epochs, so one plan / one graph launch covers all of them)."""
         perm = np.asarray(perm, dtype=np.int64)
         n = len(perm)
-        bid = np.arange(n) // batch_size
+        if epoch_len is None or epoch_len >= n:
+            bid = np.arange(n) // batch_size
+            nb = (n + batch_size - 1) // batch_size
+        else:
+            nb_e = (epoch_len + batch_size - 1) // batch_size
+            pos = np.arange(n)
+            bid = (pos % epoch_len) // batch_size + (pos // epoch_len) * nb_e
+            nb = nb_e * (n // epoch_len)
         keep = (d_len[perm] + t_len[perm]) > 0
         if not keep.all():
             perm, bid = perm[keep], bid[keep]
-        nb = (n + batch_size - 1) // batch_size
         counts = np.bincount(bid, minlength=nb)
         self.rows = perm
         self.row_off = np.zeros(nb + 1, np.int32)
@@ -204,6 +212,7 @@ class OrgEngine:
 
     def __init__(self, data: DeviceCSR, target: DeviceCSR, batch_rows, H1=256, H2=128, loss_kind=0, plan_epochs=1):
         self.data, self.target = data, target
+        self.plan_epochs = plan_epochs
         self.n_rows, self.n_enc = data.shape
         self.n_dec = target.shape[1]
         self.H1, self.H2 = H1, H2
@@ -255,6 +264,16 @@ class OrgEngine:
             o0 += nb[e] + 1
             l0 += nb[e]
         self._keep_alive += [rows_all, off_all, loss_out]
+
+    def enqueue_round(self, layout, seed, hp=None, loss_out=None):
+        """All local epochs of a round as ONE plan and ONE graph launch (layout = FastEpochLayout with epoch_len;
+        the engine must have been created with plan_epochs >= the number of epochs)."""
+        rows = to_dev(layout.rows.astype(np.int32), self.device)
+        off = to_dev(layout.row_off, self.device)
+        self.h.wait_current()
+        self.h.train_epoch(rows, off, layout.n_t, layout.n_d, keep=None, seed=int(seed), epoch_loss=loss_out,
+                           **(hp or {}))
+        self._keep_alive += [rows, off, loss_out]
 
     def params(self):
         return self.h.get_params()

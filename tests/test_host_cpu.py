@@ -212,3 +212,25 @@ def test_lazy_csr_and_pending_flush():
     org_mod.flush_pending()
     org_mod.flush_pending()
     assert seen == ['a', 'b']
+
+
+def test_whole_round_layout_equals_concatenated_epochs():
+    """FastEpochLayout(epoch_len=...) — one plan for all local epochs — lists exactly the per-epoch layouts back to back."""
+    import numpy as np
+
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import engine as E
+
+    rng = np.random.default_rng(0)
+    n, bs, ep = 103, 10, 4
+    d_len, t_len = rng.integers(0, 3, n), rng.integers(0, 4, n)
+    perms = [rng.permutation(n) for _ in range(ep)]
+    lays = [E.FastEpochLayout(p, bs, d_len, t_len) for p in perms]
+    whole = E.FastEpochLayout(np.concatenate(perms), bs, d_len, t_len, epoch_len=n)
+    assert np.array_equal(whole.rows, np.concatenate([l.rows for l in lays]))
+    base = np.cumsum([0] + [len(l.rows) for l in lays[:-1]])
+    glob = np.concatenate([l.row_off[:-1] + b for l, b in zip(lays, base)] + [np.array([sum(len(l.rows) for l in lays)])])
+    assert np.array_equal(whole.row_off, glob)
+    assert whole.active == sum([l.active for l in lays], [])
+    assert whole.d_per_batch == sum([l.d_per_batch for l in lays], [])
+    assert whole.n_t == sum(l.n_t for l in lays) and whole.n_d == sum(l.n_d for l in lays)

@@ -174,27 +174,28 @@ class FastEpochLayout:
         layout: batch ids keep counting across epochs, so one plan / one graph launch covers all of them)."""
         perm = np.asarray(perm, dtype=np.int64)
         n = len(perm)
-        if epoch_len is None or epoch_len >= n:
-            bid = np.arange(n) // batch_size
-            nb = (n + batch_size - 1) // batch_size
+        L = n if (epoch_len is None or epoch_len >= n) else int(epoch_len)
+        n_ep = n // L if L else 0
+        starts = (np.arange(0, L, batch_size)[None, :] + (np.arange(n_ep) * L)[:, None]).ravel() if n else \
+            np.zeros(0, np.int64)
+        nb = len(starts)
+        dl, tl = d_len[perm], t_len[perm]
+        keep = (dl + tl) > 0
+        if n == 0:
+            counts = np.zeros(0, np.int64)
+            d_per = np.zeros(0, np.int64)
         else:
-            nb_e = (epoch_len + batch_size - 1) // batch_size
-            pos = np.arange(n)
-            bid = (pos % epoch_len) // batch_size + (pos // epoch_len) * nb_e
-            nb = nb_e * (n // epoch_len)
-        keep = (d_len[perm] + t_len[perm]) > 0
-        if not keep.all():
-            perm, bid = perm[keep], bid[keep]
-        counts = np.bincount(bid, minlength=nb)
-        self.rows = perm
+            # rows that are dropped have neither data nor targets: the per-batch sums can run over the unfiltered order
+            d_per = np.add.reduceat(dl.astype(np.int64), starts)
+            counts = np.add.reduceat(keep.astype(np.int64), starts)
+        self.rows = perm if keep.all() else perm[keep]
         self.row_off = np.zeros(nb + 1, np.int32)
         self.row_off[1:] = np.cumsum(counts)
-        d_per = np.bincount(bid, weights=d_len[perm], minlength=nb)
         self.active = (d_per > 0).tolist()
         self.batch_rows = counts.tolist()
-        self.d_per_batch = d_per.astype(np.int64).tolist()
-        self.n_t = int(t_len[perm].sum())
-        self.n_d = int(d_len[perm].sum())
+        self.d_per_batch = d_per.tolist()
+        self.n_t = int(tl.sum())
+        self.n_d = int(dl.sum())
 
 
 def decoder_default():

@@ -96,3 +96,53 @@ def test_group_lockstep_matches_per_organization_graphs():
             assert float((a.F[k] - b.F[k]).abs().max()) <= 1e-4 * float(a.F[k].abs().max())
     a.close()
     b.close()
+
+
+def test_more_ranks_than_organizations():
+    """8 emulated ranks for 4 organizations (ranks 4-7 own nothing, as ranks 6-7 do for 18 organizations on 8 GPUs):
+    empty ranks still take part in the exchange and the replicated update; F_t equals the single-rank run bit-for-bit."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import roundloop, runner, synth
+    from dmtcdr_b200.config import make_cfg
+
+    control = "Amazon_user_implicit_ae_0_genre_assist_constant-0.1_constant"
+    make_cfg(control, device="cuda", seed=0)
+    data = synth.make_rating_data("tiny-Amazon", seed=0)
+    torch.manual_seed(0)
+    dataset = runner.fetch_dataset(data)
+    runner.process_dataset(dataset)
+    split = [s.numpy() for s in runner.split_dataset(dataset)]
+    mats = {k: (dataset[k].data, dataset[k].target) for k in dataset}
+    kw = dict(target_mode="implicit", batch_rows=50, clamp=True, ar=0.1, local_epochs=2, device="cuda:0", seed=3)
+    one = roundloop.AssistRounds(mats, split, rank=0, world=1, **kw)
+    world = 8
+    ranks = [roundloop.AssistRounds(mats, split, rank=r, world=world, **kw) for r in range(world)]
+    assert sorted(sum((r.my_orgs for r in ranks), [])) == list(range(len(split)))
+    assert any(not r.my_orgs for r in ranks)
+    for r in [one] + ranks:
+        r.round0()
+    for t in (1, 2):
+        one.run_round(t)
+        for r in ranks:
+            r.train_predict(t)
+        for r in ranks:
+            r.sync()
+        c = ranks[0].chunk
+        for k in ("train", "test"):
+            for src in range(world):
+                for dst in range(world):
+                    if dst != src:
+                        ranks[dst].state.O_full[k][src * c:(src + 1) * c].copy_(
+                            ranks[src].state.O_full[k][src * c:(src + 1) * c])
+        for r in ranks:
+            r.combine()
+        one.sync()
+        for k in ("train", "test"):
+            for r in ranks:
+                assert torch.equal(one.F[k], r.F[k])
+    m0, m7 = ranks[0].evaluate("test"), ranks[7].evaluate("test")
+    assert m0 == m7 == one.evaluate("test")
+    for r in [one] + ranks:
+        r.close()

@@ -234,3 +234,29 @@ def test_whole_round_layout_equals_concatenated_epochs():
     assert whole.active == sum([l.active for l in lays], [])
     assert whole.d_per_batch == sum([l.d_per_batch for l in lays], [])
     assert whole.n_t == sum(l.n_t for l in lays) and whole.n_d == sum(l.n_d for l in lays)
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype in include/dmt_b200.h has a ctypes declaration in native.py with the same number of arguments
+    (an arity mismatch would only show up as a crash on the GPU box)."""
+    import re
+
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import native
+
+    lib = native.load()
+    with open(os.path.join(ROOT, "include", "dmt_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    protos = re.findall(r"\b(dmt_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) > 40
+    checked = 0
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue  # exported but not bound from Python
+        assert len(fn.argtypes) == n, "{}: header has {} arguments, native.py declares {}".format(name, n,
+                                                                                                   len(fn.argtypes))
+        checked += 1
+    assert checked > 40

@@ -408,11 +408,14 @@ int launch_group_decoder(const OrgDev* orgs, int G, int b, int B, int H1, cudaSt
 int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
                              const float* A3, const float* W4, const float* b4, int H, int loss_kind,
                              const int32_t* n_targets, const int32_t* ent_off, DecChunks dc, float* gout, float* dZ3,
-                             float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st) {
+                             float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st, int blocks_hint) {
     if (n_rows_max <= 0) return 0;
     // persistent over the batch's chunks (count known only on the device); 2 blocks per SM leaves room for the other
     // organizations' graphs that run concurrently on their own streams
-    const int blocks = kNumSMs * 2;
+    // default: two blocks per SM (the kernel's 128 registers x 256 threads fill the register file with two) — the
+    // fastest for ONE organization; with many organizations per GPU fewer blocks leave room for the other
+    // organizations' kernels on the same SMs and the round gets shorter although this kernel gets longer (blocks_hint)
+    const int blocks = blocks_hint > 0 ? blocks_hint : kNumSMs * 2;
 #define DMT_DECC(V)                                                                                             \
     ae_decoder_chunk_kernel<V><<<blocks, 256, 0, st>>>(rows, indptr, indices, target, A3, W4, b4, loss_kind,   \
                                                        n_targets, ent_off, dc, gout, br)

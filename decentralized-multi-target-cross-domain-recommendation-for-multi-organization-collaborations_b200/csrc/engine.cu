@@ -12,6 +12,7 @@
 // 148 SMs even though a single 500-row batch cannot.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -76,6 +77,7 @@ struct dmt_org {
     int64_t dec_chunk_cap, dec_part_rows;
     // tensor-core decoder (decoder_tc.cu)
     int dec_mode, dec_passes;
+    int dec_blocks;  // grid of the decoder chunk kernel (0: two per SM), dmt_org_set_decoder_blocks
     int fanout;  // 1: the backward pass of a step is enqueued as parallel branches (dmt_org_set_fanout)
     float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
     // tables of per-row CSR windows at 128-column tile borders, one per target CSR seen (train targets, predict splits)
@@ -374,7 +376,7 @@ static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only
         DecChunks dc{o->t_chunk_off, o->t_chunk_row, o->t_batch_chunk, o->dz_part, o->loss_part};
         if ((rc = launch_ae_decoder_chunks(o->rows_buf, o->t_indptr, o->t_indices, o->t_val, o->a3, W4, b4, H1,
                                            DMT_LOSS_MSE, o->pt.batch_cnt, o->pt.ent_off, dc, o->gbuf, o->dz3,
-                                           o->loss_rows, B, br, st)))
+                                           o->loss_rows, B, br, st, o->dec_blocks)))
             return rc;
     }
     // Backward fan-out. Once the decoder has produced g (gbuf) and dZ3 the rest of the backward pass is a DAG, not a
@@ -561,6 +563,10 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     A(dalloc(&o->t_chunk_row, o->dec_chunk_cap)); A(dalloc(&o->t_batch_chunk, o->nb_cap + 2));
     A(dalloc(&o->dz_part, o->dec_part_rows * H1)); A(dalloc(&o->loss_part, o->dec_part_rows));
     o->dec_mode = 0; o->dec_passes = 3;
+    {
+        const char* env = getenv("DMT_DEC_BLOCKS");
+        o->dec_blocks = env ? atoi(env) : 0;
+    }
     A(dalloc(&o->tc_scratch, decoder_tc_scratch_floats(batch_rows, n_dec, H1)));
     A(dalloc(&o->gbuf, t_cap)); A(dalloc(&o->dval_ord, d_cap)); A(dalloc(&o->row_batch, o->rows_cap + 1));
     A(dalloc(&o->active, o->nb_cap + 1));
@@ -598,6 +604,17 @@ int dmt_org_destroy(dmt_org_t* o) {
 }
 
 int64_t dmt_org_num_params(const dmt_org_t* o) { return o ? o->n_params : 0; }
+
+int dmt_org_set_decoder_blocks(dmt_org_t* o, int blocks) {
+    DMT_REQUIRE(o && blocks >= 0 && blocks <= 65535, "dmt_org_set_decoder_blocks: bad argument");
+    if (o->dec_blocks != blocks && o->exec) {  // the grid is baked into the captured graph
+        cudaGraphExecDestroy(o->exec);
+        o->exec = nullptr;
+        o->g_nb = -1;
+    }
+    o->dec_blocks = blocks;
+    return 0;
+}
 
 int dmt_org_set_fanout(dmt_org_t* o, int on) {
     DMT_REQUIRE(o, "dmt_org_set_fanout: null");

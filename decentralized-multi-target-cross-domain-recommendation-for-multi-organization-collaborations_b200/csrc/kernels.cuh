@@ -150,7 +150,7 @@ struct DecChunks {
 int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const int32_t* indices, const float* target,
                              const float* A3, const float* W4, const float* b4, int H, int loss_kind,
                              const int32_t* n_targets, const int32_t* ent_off, DecChunks dc, float* gout, float* dZ3,
-                             float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st);
+                             float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st, int blocks_hint = 0);
 
 // ---------------------------------------------------------------- organization groups (one launch = all organizations)
 // Device-visible view of one organization. A group launch adds the organization as grid dimension z, so a step of

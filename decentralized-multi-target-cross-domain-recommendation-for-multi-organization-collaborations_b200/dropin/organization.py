@@ -281,6 +281,11 @@ class Organization:
                 self._eng.close()
             self._eng = E.OrgEngine(d, t, bs, enc[0], enc[1], native.LOSS_KIND[cfg['target_mode']],
                                     plan_epochs=plan_epochs)
+            # all organizations of the experiment share this GPU: with many of them the decoder chunk kernel gets the
+            # smaller grid that shortens the round (roundloop.DEC_BLOCKS_MANY_ORGS)
+            from dmtcdr_b200 import roundloop as _rl
+            n_orgs = int(cfg['num_organizations']) if 'num_organizations' in cfg else 1
+            self._eng.h.set_decoder_blocks(_rl.DEC_BLOCKS_MANY_ORGS if n_orgs > _rl.FANOUT_MAX_ORGS else 0)
             self._eng_key = key
             self._residual_buf = torch.empty(t.nnz, device=_device())
         return self._eng, d, t

@@ -81,6 +81,7 @@ def _declare(lib):
         "dmt_ae_decoder_tc": (I, [P, I, P, P, P, P, P, P, I, I, I, P, I, P, P, P, P, P, P, I, P, P]),
         "dmt_org_set_decoder_mode": (I, [P, I, I]),
         "dmt_org_set_fanout": (I, [P, I]),
+        "dmt_org_set_decoder_blocks": (I, [P, I]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
         "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, I, P]),
         "dmt_eval_blocks": (I, [P, P, P, I, I, I, I, P, P, P]),
@@ -521,6 +522,10 @@ class Org:
         code = {"gather": 0, "tc": 1}[mode]
         check(self._lib.dmt_org_set_decoder_mode(self.h, code, int(passes)), "dmt_org_set_decoder_mode")
         self.decoder_mode = mode
+
+    def set_decoder_blocks(self, blocks):
+        """Grid of the decoder chunk kernel (0: two blocks per SM); fewer blocks pay with many organizations per GPU."""
+        check(self._lib.dmt_org_set_decoder_blocks(self.h, int(blocks)), "dmt_org_set_decoder_blocks")
 
     def set_fanout(self, on):
         """Backward pass of a step as parallel graph branches (pays with few organizations per GPU)."""

@@ -24,6 +24,7 @@ from . import native
 # 5: 96.1 -> 85.5, 9: 140.4 -> 130.7; at 18 the round is throughput-bound and the shape of the step does not matter
 # (214.7 vs 215.0 once the host no longer stalls behind the compute streams).
 FANOUT_MAX_ORGS = 9
+DEC_BLOCKS_MANY_ORGS = 111  # decoder chunk grid when a rank holds more organizations than that (default 296 = 2 per SM)
 # device memory the whole-round plans of a rank may take (bytes); DMT_WHOLE_ROUND=0|1 overrides
 WHOLE_ROUND_PLAN_BUDGET = 48 << 30
 # Measured on one B200 at ML1M shape (ms per round, per-epoch -> whole-round): 3 organizations 63.0 -> 59.9, 9
@@ -101,8 +102,14 @@ class AssistRounds:
         # on private streams — both are bound by the same L2 gather traffic — so per-organization graphs stay default.
         fan = os.environ.get("DMT_FANOUT")
         fan = (len(self.my_orgs) <= FANOUT_MAX_ORGS) if fan is None else fan == "1"
+        # many organizations per GPU: a smaller grid for the register-heavy decoder chunk kernel leaves room for the
+        # other organizations' kernels (18 organizations: 214.7 ms per round with 296 blocks, 204.3 with 111, 203.9 with 74)
+        dec_blocks = os.environ.get("DMT_DEC_BLOCKS")
+        dec_blocks = (DEC_BLOCKS_MANY_ORGS if len(self.my_orgs) > FANOUT_MAX_ORGS else 0) if dec_blocks is None \
+            else int(dec_blocks)
         for k in self.my_orgs:
             self.eng[k].h.set_fanout(fan)
+            self.eng[k].h.set_decoder_blocks(dec_blocks)
         self.fanout = fan
         self.group = native.Group([self.eng[k].h for k in self.my_orgs]) if group and self.my_orgs else None
         self.cols = cols

@@ -247,6 +247,11 @@ int dmt_org_set_decoder_mode(dmt_org_t* org, int mode, int passes);
  * when a GPU holds few organizations (org-sharded runs); with many organizations per GPU their graphs already fill the
  * machine and the extra cross-branch dependencies cost more than they save (measured). Same results. */
 int dmt_org_set_fanout(dmt_org_t* org, int on);
+/* Grid of the decoder chunk kernel inside a training step: 0 (default) = two blocks per SM, the fastest for one
+ * organization alone; a rank that runs many organizations concurrently gets a shorter ROUND with one block per SM
+ * (148), because the kernel's register footprint then leaves room for the other organizations' kernels (measured at
+ * ML1M shape, 18 organizations: 214.7 -> 205.6 ms per round while the kernel itself goes from 23.6 to 32.9 us). */
+int dmt_org_set_decoder_blocks(dmt_org_t* org, int blocks);
 /* number of fp32 parameters; flat layout: W1t[n_enc*H1] b1[H1] W2[H2*H1] b2[H2] W3[H1*H2] b3[H1] W4[n_dec*H1] b4[n_dec] */
 int64_t dmt_org_num_params(const dmt_org_t* org);
 /* Copy parameters in/out (device pointers, flat layout above). set also resets the Adam state: the reference builds

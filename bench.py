@@ -249,14 +249,14 @@ def run_ours(args):
                 "step_kernel_ms": prof, "slowest_class": dom,
                 "ms_per_launch_round_grid": prof_round_grid["decoder_loss_dz3"],
                 "round_grid_note": "decoder chunk grid in the timed rounds: {} blocks (default 296)".format(
-                    roundloop.DEC_BLOCKS_MANY_ORGS if len(rounds.my_orgs) > roundloop.FANOUT_MAX_ORGS else 296),
+                    roundloop.decoder_blocks_for(len(rounds.my_orgs)) or 296),
                 "adam_GBps": n_params * 28 / (prof["clip_adam"] * 1e-3) / 1e9}
         roof["hbm_case"] = hbm_bound_case(dev, hbm)
         # the decoder's other form (tcgen05 GEMMs, 3xTF32): same batch, same plan, per-class timings + D1 alone
         eng.set_decoder("tc")
         prof_tc = eng.h.profile_step(b=0, reps=20)
         eng.set_decoder(E.decoder_default() if eng.target.sorted else "gather")
-        eng.h.set_decoder_blocks(roundloop.DEC_BLOCKS_MANY_ORGS if len(rounds.my_orgs) > roundloop.FANOUT_MAX_ORGS else 0)
+        eng.h.set_decoder_blocks(roundloop.decoder_blocks_for(len(rounds.my_orgs)))
         roof["tc_decoder"] = tc_decoder_case(rounds.state.y["train"], dev, prof, prof_tc)
 
     # ---- end to end through the drop-in API with host buffers (single-process API: measured on rank 0's GPU)

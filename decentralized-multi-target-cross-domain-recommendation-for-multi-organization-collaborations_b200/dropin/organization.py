@@ -20,8 +20,6 @@ from dmtcdr_b200.config import cfg
 import models
 
 _DEVICE_CSR = {}
-import os as _os
-_NO_FASTPATH = _os.environ.get("DMT_NO_FASTPATH") == "1"
 _CSR_IDENTITY = {}  # (id(indptr), id(indices)) -> (indptr, indices, shape, nnz, content key)
 
 
@@ -29,8 +27,6 @@ def _structure_key(m):
     """Content key of the CSR structure. CRC-ing the index arrays costs ~1 ms per call at ML1M shape and the drivers
     hand the same arrays back ~100 times per round, so the arrays' identity is tried first; the cache holds references
     to them, which keeps their ids unique for as long as an entry lives."""
-    if _NO_FASTPATH:
-        return E.csr_key(m)
     ip, ix = m.indptr, m.indices
     fk = (id(ip), id(ix))
     ent = _CSR_IDENTITY.get(fk)
@@ -285,7 +281,7 @@ class Organization:
             # smaller grid that shortens the round (roundloop.DEC_BLOCKS_MANY_ORGS)
             from dmtcdr_b200 import roundloop as _rl
             n_orgs = int(cfg['num_organizations']) if 'num_organizations' in cfg else 1
-            self._eng.h.set_decoder_blocks(_rl.DEC_BLOCKS_MANY_ORGS if n_orgs > _rl.FANOUT_MAX_ORGS else 0)
+            self._eng.h.set_decoder_blocks(_rl.decoder_blocks_for(n_orgs))
             self._eng_key = key
             self._residual_buf = torch.empty(t.nnz, device=_device())
         return self._eng, d, t

@@ -25,6 +25,17 @@ from . import native
 # (214.7 vs 215.0 once the host no longer stalls behind the compute streams).
 FANOUT_MAX_ORGS = 9
 DEC_BLOCKS_MANY_ORGS = 111  # decoder chunk grid when a rank holds more organizations than that (default 296 = 2 per SM)
+
+
+def decoder_blocks_for(n_orgs):
+    """Grid of the decoder chunk kernel by the number of organizations that share the GPU (0 = the kernel's default,
+    two blocks per SM). Measured at ML1M shape, ms per round: 18 organizations 296 -> 214.7, 148 -> 205.5, 111 -> 204.3;
+    9 organizations 296 -> 106.8, 222 -> 105.6, 148 -> 104.4."""
+    if n_orgs > FANOUT_MAX_ORGS:
+        return DEC_BLOCKS_MANY_ORGS
+    if n_orgs >= 6:
+        return 148
+    return 0
 # device memory the whole-round plans of a rank may take (bytes); DMT_WHOLE_ROUND=0|1 overrides
 WHOLE_ROUND_PLAN_BUDGET = 48 << 30
 # Measured on one B200 at ML1M shape (ms per round, per-epoch -> whole-round): 3 organizations 63.0 -> 59.9, 9
@@ -105,8 +116,7 @@ class AssistRounds:
         # many organizations per GPU: a smaller grid for the register-heavy decoder chunk kernel leaves room for the
         # other organizations' kernels (18 organizations: 214.7 ms per round with 296 blocks, 204.3 with 111, 203.9 with 74)
         dec_blocks = os.environ.get("DMT_DEC_BLOCKS")
-        dec_blocks = (DEC_BLOCKS_MANY_ORGS if len(self.my_orgs) > FANOUT_MAX_ORGS else 0) if dec_blocks is None \
-            else int(dec_blocks)
+        dec_blocks = decoder_blocks_for(len(self.my_orgs)) if dec_blocks is None else int(dec_blocks)
         for k in self.my_orgs:
             self.eng[k].h.set_fanout(fan)
             self.eng[k].h.set_decoder_blocks(dec_blocks)

@@ -506,6 +506,8 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
                    void* stream) {
     DMT_REQUIRE(out && n_rows > 0 && n_enc > 0 && n_dec > 0 && batch_rows > 0, "dmt_org_create: bad sizes");
     DMT_REQUIRE(H1 % 128 == 0 && H1 <= 512 && H2 > 0, "dmt_org_create: H1 must be 128/256/384/512");
+    // the flat layout puts b2, W3, b3, W4 behind H2-sized blocks and every sub-view is read with 128-bit loads
+    DMT_REQUIRE(H2 % 4 == 0, "dmt_org_create: H2 must be a multiple of 4");
     DMT_REQUIRE(d_nnz >= 0 && t_nnz >= 0 && t_nnz < (1LL << 31) - 2 && d_nnz < (1LL << 31) - 2,
                 "dmt_org_create: nnz must fit int32");
     int rc = dmt_check_device();
@@ -574,7 +576,8 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     if (o->sort_temp_bytes < (1 << 20)) o->sort_temp_bytes = 1 << 20;
     A(dalloc(reinterpret_cast<char**>(&o->sort_temp), o->sort_temp_bytes));
     A(dalloc(&o->rows_buf, o->rows_cap)); A(dalloc(&o->row_off_buf, o->nb_cap + 1));
-    A(dalloc(&o->keep_buf, (int64_t)o->rows_cap * H2)); A(dalloc(&o->seed_dev, 1)); A(dalloc(&o->loss_buf, o->nb_cap));
+    o->keep_buf = nullptr;  // explicit dropout masks are a parity-test input: allocated on first use (train_epoch)
+    A(dalloc(&o->seed_dev, 1)); A(dalloc(&o->loss_buf, o->nb_cap));
     A(dalloc(&o->partial, kNormBlocks)); A(dalloc(&o->sc, 1)); A(dalloc(&o->step_dev, 1));
 #undef A
     {
@@ -682,7 +685,14 @@ int dmt_org_train_epoch(dmt_org_t* o, const int32_t* rows, const int32_t* row_of
     cudaStream_t st = o->st;
     DMT_CUDA(cudaMemcpyAsync(o->rows_buf, rows, (size_t)n_rows_total * 4, cudaMemcpyDeviceToDevice, st));
     DMT_CUDA(cudaMemcpyAsync(o->row_off_buf, row_off, (size_t)(n_batches + 1) * 4, cudaMemcpyDeviceToDevice, st));
-    if (keep) DMT_CUDA(cudaMemcpyAsync(o->keep_buf, keep, (size_t)n_rows_total * o->H2, cudaMemcpyDeviceToDevice, st));
+    if (keep) {
+        if (!o->keep_buf) {
+            int rc_k = dalloc(&o->keep_buf, (int64_t)o->rows_cap * o->H2);
+            if (rc_k) return rc_k;
+            if (o->exec) { cudaGraphExecDestroy(o->exec); o->exec = nullptr; o->g_nb = -1; }  // pointer is baked in
+        }
+        DMT_CUDA(cudaMemcpyAsync(o->keep_buf, keep, (size_t)n_rows_total * o->H2, cudaMemcpyDeviceToDevice, st));
+    }
     DMT_CUDA(cudaMemcpyAsync(o->seed_dev, &seed, sizeof(seed), cudaMemcpyHostToDevice, st));
     int rc = 0;
     AdamHyper hp{lr, beta1, beta2, eps, weight_decay, max_norm};
@@ -823,6 +833,7 @@ struct dmt_group {
     std::vector<OrgDev> views;  // what d_orgs currently holds
     OrgDev* d_orgs;
     cudaStream_t st;
+    bool own_stream;
     cudaEvent_t ev;
     cudaGraphExec_t exec;
     long long g_kernels;
@@ -831,6 +842,14 @@ struct dmt_group {
     int64_t n_params_max;
     int n_enc_max;
 };
+
+static void group_free(dmt_group* g) {
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->d_orgs) cudaFree(g->d_orgs);
+    if (g->ev) cudaEventDestroy(g->ev);
+    if (g->own_stream && g->st) cudaStreamDestroy(g->st);
+    delete g;
+}
 
 static OrgDev org_view(dmt_org* o) {
     OrgDev v{};
@@ -894,6 +913,7 @@ int dmt_group_create(dmt_group_t** out, dmt_org_t* const* orgs, int n, void* str
     dmt_group* g = new (std::nothrow) dmt_group();
     if (!g) return DMT_E_NOMEM;
     g->exec = nullptr; g->g_nb = -1; g->d_orgs = nullptr; g->n_params_max = 0; g->n_enc_max = 0;
+    g->st = nullptr; g->own_stream = false; g->ev = nullptr;
     for (int i = 0; i < n; ++i) {
         dmt_org* o = orgs[i];
         if (!o || o->n_rows != orgs[0]->n_rows || o->H1 != orgs[0]->H1 || o->H2 != orgs[0]->H2 ||
@@ -906,10 +926,16 @@ int dmt_group_create(dmt_group_t** out, dmt_org_t* const* orgs, int n, void* str
         if (o->n_params > g->n_params_max) g->n_params_max = o->n_params;
         if (o->n_enc > g->n_enc_max) g->n_enc_max = o->n_enc;
     }
+    cudaError_t e = cudaSuccess;
     if (stream) g->st = as_stream(stream);
-    else DMT_CUDA(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
-    DMT_CUDA(cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming));
-    DMT_CUDA(cudaMalloc(reinterpret_cast<void**>(&g->d_orgs), sizeof(OrgDev) * n));
+    else if ((e = cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking)) == cudaSuccess) g->own_stream = true;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&g->d_orgs), sizeof(OrgDev) * n);
+    if (e != cudaSuccess) {
+        group_free(g);
+        set_error(cudaGetErrorString(e));
+        return (int)e;
+    }
     *out = g;
     return 0;
 }
@@ -917,10 +943,7 @@ int dmt_group_create(dmt_group_t** out, dmt_org_t* const* orgs, int n, void* str
 int dmt_group_destroy(dmt_group_t* g) {
     if (!g) return 0;
     cudaStreamSynchronize(g->st);
-    if (g->exec) cudaGraphExecDestroy(g->exec);
-    cudaFree(g->d_orgs);
-    cudaEventDestroy(g->ev);
-    delete g;
+    group_free(g);
     return 0;
 }
 

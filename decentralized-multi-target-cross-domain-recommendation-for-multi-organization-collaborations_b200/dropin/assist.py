@@ -108,8 +108,8 @@ class Assist:
     def update(self, organization_outputs, iter):
         """F_t = F_{t-1} + eta[idx] * sum_j softmax(w)_j out_j for every owner, with the optional L-BFGS fit of eta / w
         on the train split and partial alignment (src/assist.py:81-179)."""
-        if 'cs' in cfg:
-            raise NotImplementedError("cold-start ('cs') runs are out of scope (DESIGN.md)")
+        if 'cs' in cfg and float(cfg['cs']) < 1:
+            raise NotImplementedError("cold-start ('cs' < 1) runs are out of scope (DESIGN.md)")
         st = self._mtal()
         import organization as _org_mod
         for k in organization_outputs[0]:

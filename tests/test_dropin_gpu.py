@@ -146,3 +146,26 @@ def test_cpu_tensors_fail_loudly(dropin):
     b = dict(fx.group("b0/in"))
     with pytest.raises(native.NativeError):
         model(b)
+
+
+def test_ml1m_shape_round_vs_oracle(dropin):
+    """One assistance round at the BENCHMARK's own shape (synthetic ML1M: 6040 x 3706, 900 188 train ratings, 18 genre
+    organizations, 500-row batches, 1 local epoch) through the drop-in API with the reference-identical RNG, against
+    the oracle's replay of the same experiment (oracle/replay.py, pinned to the reference by tests/golden): global
+    prediction F_1 within 5e-4 of its largest magnitude, test RMSE within 1e-4 (BASELINE.json north_star). Every batch
+    here has rows with more than 128 targets and columns with more than 64 entries, i.e. the multi-chunk decoder /
+    segment kernels that the timed rounds run (reference src/models/ae.py:135-142, src/organization.py:149-162)."""
+    from dmtcdr_b200 import runner, synth
+    from oracle import replay
+
+    control = "ML1M_user_explicit_ae_0_genre_assist_constant-0.1_constant"
+    data = synth.make_rating_data("ML1M", seed=0)
+    got = runner.run_assist_experiment(data, control, seed=0, local_epochs=1, rounds=1, rng="reference")
+    ref = replay.run_experiment(data, control, seed=0, local_epochs=1, rounds=1)
+    for i in range(18):
+        assert np.array_equal(got["data_split"][i], ref["data_split"][i])
+    for t in (0, 1):
+        for k in ("train", "test"):
+            assert rel_err(got["F"][t][k], ref["F"][t][k]) < (1e-6 if t == 0 else 5e-4), (t, k)
+        r_got, r_ref = got["metrics"][t]["test/RMSE"], ref["metrics"][t]["test/RMSE"]
+        assert abs(r_got - r_ref) <= 1e-4, (t, r_got, r_ref)

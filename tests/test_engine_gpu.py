@@ -154,6 +154,121 @@ def test_train_epochs_and_predict(nat, seed, bs, n_rows, n_dec, decoder):
     org.close()
 
 
+def zipf_csr(rng, n_rows, n_cols, per_row_lo, per_row_hi, heavy_rows=(), heavy_len=1500, values="normal"):
+    """Benchmark-like sparsity: row lengths spread between per_row_lo and per_row_hi (plus a few heavy rows, the
+    ML1M users with ~2000 ratings), columns drawn without replacement from a Zipf popularity law so that the popular
+    columns appear in far more than 64 rows of one 500-row batch."""
+    w = 1.0 / np.arange(1, n_cols + 1) ** 0.9
+    w = w[rng.permutation(n_cols)]
+    w /= w.sum()
+    lens = rng.integers(per_row_lo, per_row_hi + 1, size=n_rows)
+    for r in heavy_rows:
+        lens[r] = heavy_len
+    indptr = np.zeros(n_rows + 1, np.int64)
+    indptr[1:] = np.cumsum(lens)
+    indices = np.empty(indptr[-1], np.int32)
+    for r in range(n_rows):
+        indices[indptr[r]:indptr[r + 1]] = np.sort(rng.choice(n_cols, size=lens[r], replace=False, p=w))
+    if values == "rating":
+        data = rng.integers(1, 6, size=indptr[-1]).astype(np.float32)
+    else:
+        data = rng.normal(size=indptr[-1]).astype(np.float32)
+        data[data == 0] = 0.5
+    return csr_matrix((data, indices, indptr.astype(np.int32)), shape=(n_rows, n_cols))
+
+
+def chunk_census(T, batches, dec_chunk=128, seg_chunk=64):
+    """(rows that span several decoder chunks, (batch, column) segments that span several reduction chunks)."""
+    multi_rows = multi_segs = 0
+    for rows in batches:
+        rows = np.asarray(rows)
+        tl = T.indptr[rows + 1] - T.indptr[rows]
+        multi_rows += int((tl > dec_chunk).sum())
+        cols = np.concatenate([T.indices[T.indptr[r]:T.indptr[r + 1]] for r in rows])
+        multi_segs += int((np.bincount(cols) > seg_chunk).sum())
+    return multi_rows, multi_segs
+
+
+@pytest.mark.parametrize("mode", ["epoch", "epoch_fanout", "round"])
+@pytest.mark.parametrize("decoder", ["gather", "tc"])
+@pytest.mark.parametrize("shape", ["ml1m_batch", "zipf_wide"])
+def test_train_benchmark_shape(nat, shape, decoder, mode):
+    """The paths the benchmark runs (VERDICT r1 'parity hole'): 500-row batches over 3706 target columns with rows of
+    far more than 128 targets (several decoder chunks + ae_decoder_finish summing dz_part) and popular columns in far
+    more than 64 rows of a batch (multi-chunk segments + segment_finish), against the oracle's Organization.train /
+    predict (reference src/organization.py:140-217, src/models/ae.py:135-142). Per-epoch plans with and without the
+    backward fan-out, and the whole-round plan (one plan, one graph for all epochs)."""
+    rng = np.random.default_rng(11 if shape == "ml1m_batch" else 12)
+    if shape == "ml1m_batch":   # two ML1M-shape batches per epoch: 1000 x 3706, ~150 targets per row
+        n_rows, n_enc, n_dec, bs, lo, hi = 1000, 206, 3706, 500, 20, 280
+        heavy = (3, 500, 777)
+    else:                       # fewer, much longer rows over a wider item space; three batches, the last one ragged
+        n_rows, n_enc, n_dec, bs, lo, hi = 700, 160, 6000, 300, 150, 700
+        heavy = (5, 650)
+    D = rand_csr(rng, n_rows, n_enc, 0.03, empty_rows=(7, 8))
+    T = zipf_csr(rng, n_rows, n_dec, lo, hi, heavy_rows=heavy, heavy_len=1900)
+    torch.manual_seed(5)
+    p0 = replay.init_ae_params(n_enc, n_dec)
+    n_epochs = 2
+    epoch_batches, masks, keep_epochs = [], [], []
+    for e in range(n_epochs):
+        perm = rng.permutation(n_rows)
+        batches = [np.sort(perm[s:s + bs]) for s in range(0, n_rows, bs)]
+        epoch_batches.append(batches)
+        ke = [torch.from_numpy((rng.random((len(b), 128)) < 0.5).astype(np.float32)) for b in batches]
+        keep_epochs.append(ke)
+        masks += ke
+    multi_rows, multi_segs = chunk_census(T, epoch_batches[0])
+    assert multi_rows > 100 and multi_segs > 100, (multi_rows, multi_segs)  # the multi-chunk paths really run
+    ref_p, ref_losses = train.train_org_ae(p0, D, T, "user", "explicit", epoch_batches, masks)
+    d_csr = (cu(D.indptr, torch.int32), cu(D.indices, torch.int32), cu(D.data))
+    t_csr = (cu(T.indptr, torch.int32), cu(T.indices, torch.int32))
+    org = nat.Org(n_rows, n_enc, n_dec, 256, 128, d_csr, t_csr, bs, 0, plan_epochs=n_epochs if mode == "round" else 1)
+    org.set_decoder_mode(decoder)
+    org.set_fanout(mode == "epoch_fanout")
+    org.wait_current()
+    org.set_params(flat_params(p0).cuda())
+    tval = cu(T.data)
+    org.set_target(tval)
+    nb = len(epoch_batches[0])
+    if mode == "round":
+        rows_a = np.concatenate([np.concatenate(b) for b in epoch_batches])
+        off = np.concatenate([[0], np.cumsum([len(r) for b in epoch_batches for r in b])])
+        keep = torch.cat([k for ke in keep_epochs for k in ke]).to(torch.uint8).cuda()
+        loss = torch.zeros(nb * n_epochs, device="cuda")
+        org.train_epoch(cu(rows_a, torch.int32), cu(off, torch.int32), int(T.nnz) * n_epochs, int(D.nnz) * n_epochs,
+                        keep=keep, epoch_loss=loss)
+        org.sync()
+        got_losses = loss.cpu().tolist()
+    else:
+        got_losses = []
+        for e, batches in enumerate(epoch_batches):
+            rows_a = np.concatenate(batches)
+            off = np.concatenate([[0], np.cumsum([len(r) for r in batches])])
+            keep = torch.cat(keep_epochs[e]).to(torch.uint8).cuda()
+            loss = torch.zeros(nb, device="cuda")
+            org.train_epoch(cu(rows_a, torch.int32), cu(off, torch.int32), int(T.nnz), int(D.nnz), keep=keep,
+                            epoch_loss=loss)
+            org.sync()
+            got_losses += loss.cpu().tolist()
+    assert len(got_losses) == len(ref_losses)
+    assert rel_err(got_losses, ref_losses) < 1e-5
+    got_p = unflat_params(org.get_params().cpu(), n_enc, n_dec)
+    org.sync()
+    tol_p = 5e-4 if decoder == "gather" else 1e-3
+    for k, v in ref_p.items():
+        assert rel_err(got_p[k], v) < tol_p, k
+    T2 = zipf_csr(rng, n_rows, n_dec, 5, 60, heavy_rows=(1,), heavy_len=900)
+    ref_pred = train.predict_org_ae(ref_p, D, T2, "user", "explicit", bs)
+    out = torch.zeros(T2.nnz, device="cuda")
+    t2 = (cu(T2.indptr, torch.int32), cu(T2.indices, torch.int32))
+    org.set_params(flat_params(ref_p).cuda())
+    org.predict(d_csr, t2, n_rows, out)
+    org.sync()
+    assert rel_err(out.cpu(), ref_pred) < 2e-5
+    org.close()
+
+
 def test_device_dropout_is_a_fair_coin(nat):
     """Without explicit keep-masks the engine draws its own: training must still run and reduce the loss."""
     rng = np.random.default_rng(3)

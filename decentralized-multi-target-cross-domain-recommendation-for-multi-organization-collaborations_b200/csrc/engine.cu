@@ -101,6 +101,18 @@ struct dmt_org {
     // backward fan-out: auxiliary streams and fork/join events (parallel branches of the captured epoch graph)
     cudaStream_t aux[3];
     cudaEvent_t fev[8];
+    // fused six-launch step (fused.cu): transposed shadows of W2 / W3, plan-time metadata, arrival counters
+    int step_mode;  // 1: fused (default when H1 = 256, H2 = 128 and the gather decoder), 0: classic 20-kernel step
+    float *W2t, *W3t;
+    int4* dec_meta;
+    int32_t* row_cnt;
+    float* g_sorted;
+    int4 *t_seg_meta, *d_seg_meta;
+    int32_t *t_row_sorted, *d_row_sorted, *t_inv_perm;
+    float* d_val_sorted;
+    int32_t *t_seg_cnt, *d_seg_cnt;
+    float *part_db, *part_dw;
+    int32_t *dw_cnt, *norm_ticket;
     // graph cache
     cudaGraphExec_t exec;
     long long g_kernels;  // our kernel launches captured in the graph
@@ -320,13 +332,81 @@ static int build_plan(dmt_org* o, int n, int nb, int64_t n_t, int64_t n_d, cudaS
                                                                         s.batch_chunk_off);
         DMT_LAUNCH_CHECK();
     }
+    if (o->step_mode == 1) {  // per-chunk metadata and sorted-order copies for the fused step (fused.cu)
+        FusedPlanArgs a{};
+        a.dec_chunk_cap = n_t / kDecChunk + n + 1;
+        if (a.dec_chunk_cap > o->dec_chunk_cap) a.dec_chunk_cap = o->dec_chunk_cap;
+        a.n_rows = n;
+        a.t_chunk_off = o->t_chunk_off; a.t_chunk_row = o->t_chunk_row; a.rows = o->rows_buf; a.row_off = o->row_off_buf;
+        a.row_batch = o->row_batch; a.t_indptr = o->t_indptr; a.t_ent_off = o->pt.ent_off; a.dec_meta = o->dec_meta;
+        a.t = FusedPlanSide{n_t, o->n_dec, o->pt.n_seg, o->pt.seg_off, o->pt.seg_key, o->pt.seg_chunk_off, o->pt.perm,
+                            o->pt.ent_row, nullptr, o->t_seg_meta, o->t_row_sorted, nullptr, o->t_inv_perm};
+        a.d = FusedPlanSide{n_d, o->n_enc, o->pd.n_seg, o->pd.seg_off, o->pd.seg_key, o->pd.seg_chunk_off, o->pd.perm,
+                            o->pd.ent_row, o->dval_ord, o->d_seg_meta, o->d_row_sorted, o->d_val_sorted, nullptr};
+        if ((rc = launch_plan_fused(a, st))) return rc;
+    }
     return 0;
 }
 
 // ---------------------------------------------------------------- one training step (enqueue only)
 enum StepClass { K_ENC = 0, K_DENSE_FWD, K_ZERO, K_DEC, K_SEG_W4, K_DENSE_BWD, K_SEG_W1, K_NORM, K_ADAM, K_NCLASS };
 
+// The fused step (fused.cu): forward rows -> decoder chunks -> {backward rows | dW4 segments} ->
+// {dW3 / dW2 tiles | bias gradients | dW1 segments} -> norm + scalars -> Adam. `only` profiles one launch class.
+static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only) {
+    cudaStream_t st = o->st;
+    const int B = o->batch_rows;
+    const BatchRef br{o->row_off_buf, o->active, b, 0, 0};
+    float *W1t = o->P + o->oW1, *b1 = o->P + o->ob1, *W2 = o->P + o->oW2, *b2 = o->P + o->ob2;
+    float *W3 = o->P + o->oW3, *b3 = o->P + o->ob3, *W4 = o->P + o->oW4, *b4 = o->P + o->ob4;
+    float* G = o->G;
+    int rc;
+    Dropout drop;
+    drop.keep = use_keep ? o->keep_buf : nullptr;
+    drop.seed_dev = o->seed_dev;
+    drop.step_dev = o->step_dev;
+    drop.row_base = o->row_off_buf;
+    drop.b = b;
+    drop.scale = 2.0f;  // nn.Dropout(p=0.5), reference src/models/ae.py:81
+    drop.p = 0.5f;
+    drop.enabled = 1;
+#define WANT(cls) (only < 0 || only == (cls))
+    if (WANT(K_ENC)) {
+        FusedFwd f{br, o->rows_buf, o->d_indptr, o->d_indices, o->d_val, W1t, b1, o->W2t, b2, o->W3t, b3,
+                   o->a1, o->a2, o->c, o->a3, drop};
+        if ((rc = launch_fused_fwd(f, B, st))) return rc;
+    }
+    if (WANT(K_DEC)) {
+        FusedDec d{br, o->dec_meta, o->t_batch_chunk, o->pt.batch_cnt, o->t_indices, o->t_val, o->t_inv_perm,
+                   o->a3, W4, b4, o->g_sorted, o->dz3, o->loss_rows, o->dz_part, o->loss_part, o->row_cnt};
+        if ((rc = launch_fused_dec(d, o->dec_blocks, st))) return rc;
+    }
+    if (WANT(K_SEG_W4)) {
+        FusedBwd w{br, o->pt.len, o->dz3, W3, W2, o->a1, o->a2, o->dz2, o->dz1, o->part_db, drop};
+        FusedSeg s{o->t_seg_meta, o->pt.batch_chunk_off, o->t_row_sorted, o->g_sorted, o->pt.part, o->pt.part_bias,
+                   o->t_seg_cnt, o->active, b};
+        if ((rc = launch_fused_bwd_phase(w, s, o->a3, G + o->oW4, G + o->ob4, B, o->n_dec * 2, st))) return rc;
+    }
+    if (WANT(K_DENSE_BWD)) {
+        FusedGrad g{br, o->pt.len, o->dz3, o->dz2, o->c, o->a1, o->part_db, G, o->oW2, o->oW3, o->ob1, o->ob2, o->ob3,
+                    o->part_dw, o->dw_cnt};
+        FusedSeg s{o->d_seg_meta, o->pd.batch_chunk_off, o->d_row_sorted, o->d_val_sorted, o->pd.part, o->pd.part_bias,
+                   o->d_seg_cnt, o->active, b};
+        if ((rc = launch_fused_grad_phase(g, s, o->dz1, G + o->oW1, o->n_enc * 2, st))) return rc;
+    }
+    if (WANT(K_NORM))
+        if ((rc = launch_norm_prepare(G, o->n_params, o->partial, o->norm_ticket, o->sc, hp, o->step_dev, o->loss_rows,
+                                      o->pt.len, o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
+            return rc;
+    if (WANT(K_ADAM))
+        if ((rc = launch_adam_shadow(o->P, G, o->M, o->V, o->n_params, o->sc, hp, o->oW2, o->oW3, o->W2t, o->W3t, st)))
+            return rc;
+#undef WANT
+    return 0;
+}
+
 static int enqueue_step(dmt_org* o, int b, bool use_keep, AdamHyper hp, int only = -1) {
+    if (o->step_mode == 1 && o->dec_mode == 0) return enqueue_step_fused(o, b, use_keep, hp, only);
     cudaStream_t st = o->st;
     const int B = o->batch_rows, H1 = o->H1, H2 = o->H2;
     BatchRef br{o->row_off_buf, o->active, b, 0, 0};
@@ -467,6 +547,20 @@ static TcTab tile_tab_for(dmt_org* o, const int32_t* indptr, const int32_t* indi
     return TcTab{tab, 2};
 }
 
+// W2t / W3t follow P: after every write of P that does not go through the fused Adam kernel
+static int refresh_shadows(dmt_org* o) {
+    if (o->W2t == nullptr) return 0;
+    return launch_shadow_refresh(o->P + o->oW2, o->P + o->oW3, o->W2t, o->W3t, o->st);
+}
+
+static void drop_graph(dmt_org* o) {
+    if (o->exec) {
+        cudaGraphExecDestroy(o->exec);
+        o->exec = nullptr;
+    }
+    o->g_nb = -1;
+}
+
 static bool same_hp(const AdamHyper& a, const AdamHyper& b) {
     return a.lr == b.lr && a.beta1 == b.beta1 && a.beta2 == b.beta2 && a.eps == b.eps &&
            a.weight_decay == b.weight_decay && a.max_norm == b.max_norm;
@@ -484,6 +578,10 @@ static int free_all(dmt_org* o) {
     for (int i = 0; i < o->n_tabs; ++i) cudaFree(o->tabs[i].tab);
     cudaFree(o->rows_buf); cudaFree(o->row_off_buf); cudaFree(o->keep_buf); cudaFree(o->seed_dev);
     cudaFree(o->loss_buf); cudaFree(o->partial); cudaFree(o->sc); cudaFree(o->step_dev);
+    cudaFree(o->W2t); cudaFree(o->W3t); cudaFree(o->dec_meta); cudaFree(o->row_cnt); cudaFree(o->g_sorted);
+    cudaFree(o->t_seg_meta); cudaFree(o->d_seg_meta); cudaFree(o->t_row_sorted); cudaFree(o->d_row_sorted);
+    cudaFree(o->t_inv_perm); cudaFree(o->d_val_sorted); cudaFree(o->t_seg_cnt); cudaFree(o->d_seg_cnt);
+    cudaFree(o->part_db); cudaFree(o->part_dw); cudaFree(o->dw_cnt); cudaFree(o->norm_ticket);
     if (o->ev) cudaEventDestroy(o->ev);
     for (int i = 0; i < 3; ++i) if (o->aux[i]) cudaStreamDestroy(o->aux[i]);
     for (int i = 0; i < kForkEvents; ++i) if (o->fev[i]) cudaEventDestroy(o->fev[i]);
@@ -579,6 +677,28 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     o->keep_buf = nullptr;  // explicit dropout masks are a parity-test input: allocated on first use (train_epoch)
     A(dalloc(&o->seed_dev, 1)); A(dalloc(&o->loss_buf, o->nb_cap));
     A(dalloc(&o->partial, kNormBlocks)); A(dalloc(&o->sc, 1)); A(dalloc(&o->step_dev, 1));
+    // fused step: usable for the reference AE shape; batch_rows <= 512 keeps the dW tiles at <= 8 row slices
+    o->step_mode = (H1 == 256 && H2 == 128 && batch_rows <= 8 * kDwSlice &&
+                    (int64_t)n_dec <= (int64_t)kFusedMaxRowChunks * kDecChunk) ? 1 : 0;
+    {
+        const char* env = getenv("DMT_STEP");
+        if (env && strcmp(env, "classic") == 0) o->step_mode = 0;
+    }
+    if (H1 == 256 && H2 == 128) {
+        A(dalloc(&o->W2t, (int64_t)H1 * H2)); A(dalloc(&o->W3t, (int64_t)H1 * H2));
+        A(dalloc(&o->dec_meta, o->dec_chunk_cap)); A(dalloc(&o->row_cnt, batch_rows)); A(dalloc(&o->g_sorted, t_cap));
+        A(dalloc(&o->t_seg_meta, o->pt.chunk_cap)); A(dalloc(&o->d_seg_meta, o->pd.chunk_cap));
+        A(dalloc(&o->t_row_sorted, t_cap)); A(dalloc(&o->d_row_sorted, d_cap)); A(dalloc(&o->t_inv_perm, t_cap));
+        A(dalloc(&o->d_val_sorted, d_cap));
+        A(dalloc(&o->t_seg_cnt, o->pt.part_rows)); A(dalloc(&o->d_seg_cnt, o->pd.part_rows));
+        A(dalloc(&o->part_db, (int64_t)((batch_rows + kFusedRows - 1) / kFusedRows) * kDbPartStride));
+        A(dalloc(&o->part_dw, (int64_t)16 * 8 * 4096)); A(dalloc(&o->dw_cnt, 16)); A(dalloc(&o->norm_ticket, 1));
+        cudaMemsetAsync(o->row_cnt, 0, (size_t)batch_rows * 4, o->st);
+        cudaMemsetAsync(o->t_seg_cnt, 0, (size_t)o->pt.part_rows * 4, o->st);
+        cudaMemsetAsync(o->d_seg_cnt, 0, (size_t)o->pd.part_rows * 4, o->st);
+        cudaMemsetAsync(o->dw_cnt, 0, 16 * 4, o->st);
+        cudaMemsetAsync(o->norm_ticket, 0, 4, o->st);
+    }
 #undef A
     {
         cudaError_t e = cudaEventCreateWithFlags(&o->ev, cudaEventDisableTiming);
@@ -638,11 +758,27 @@ int dmt_org_set_decoder_mode(dmt_org_t* o, int mode, int passes) {
         o->exec = nullptr;
         o->g_nb = -1;
     }
+    const bool to_fused = o->step_mode == 1 && o->dec_mode == 1 && mode == 0;
     o->dec_mode = mode;
     o->dec_passes = passes;
     if (mode == 1 && o->train_tab.tab == nullptr) o->train_tab = tile_tab_for(o, o->t_indptr, o->t_indices, o->n_rows);
+    if (to_fused) return refresh_shadows(o);  // the classic step's Adam does not maintain them
     return 0;
 }
+
+int dmt_org_set_step_mode(dmt_org_t* o, int mode) {
+    DMT_REQUIRE(o && (mode == 0 || mode == 1), "dmt_org_set_step_mode: bad argument");
+    DMT_REQUIRE(mode == 0 || (o->W2t != nullptr && o->batch_rows <= 8 * kDwSlice &&
+                              (int64_t)o->n_dec <= (int64_t)kFusedMaxRowChunks * kDecChunk),
+                "dmt_org_set_step_mode: the fused step needs H1 = 256, H2 = 128, batch_rows <= 512");
+    if (o->step_mode == mode) return 0;
+    drop_graph(o);  // the shape of the graph changes; plans of the fused step carry extra tables
+    o->step_mode = mode;
+    if (mode == 1) return refresh_shadows(o);
+    return 0;
+}
+
+int dmt_org_step_mode(const dmt_org_t* o) { return o ? (o->step_mode == 1 && o->dec_mode == 0 ? 1 : 0) : 0; }
 
 int dmt_org_set_params(dmt_org_t* o, const float* flat) {
     DMT_REQUIRE(o && flat, "dmt_org_set_params: null");
@@ -651,7 +787,7 @@ int dmt_org_set_params(dmt_org_t* o, const float* flat) {
     DMT_CUDA(cudaMemsetAsync(o->V, 0, (size_t)o->n_params * 4, o->st));
     DMT_CUDA(cudaMemsetAsync(o->G, 0, (size_t)o->n_params * 4, o->st));
     DMT_CUDA(cudaMemsetAsync(o->step_dev, 0, sizeof(int), o->st));
-    return 0;
+    return refresh_shadows(o);
 }
 
 int dmt_org_get_params(const dmt_org_t* o, float* flat) {
@@ -739,10 +875,16 @@ int dmt_org_predict(dmt_org_t* o, const int32_t* d_indptr, const int32_t* d_indi
         int hi = lo + o->act_rows < n_rows ? lo + o->act_rows : n_rows;
         BatchRef br = batch_by_value(lo, hi);
         int m = hi - lo;
-        if ((rc = launch_ae_encoder_fwd(o->iota_rows, d_indptr, d_indices, d_val, W1t, b1, H1, o->a1, m, br, st)))
-            return rc;
-        if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, nullptr, nodrop, m, H2, H1, 1, br, st))) return rc;
-        if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, m, H1, H2, 1, br, st))) return rc;
+        if (o->step_mode == 1 && o->dec_mode == 0) {  // encoder + both dense layers in one row-local launch
+            FusedFwd f{br, o->iota_rows, d_indptr, d_indices, d_val, W1t, b1, o->W2t, b2, o->W3t, b3,
+                       nullptr, nullptr, nullptr, o->a3, nodrop};
+            if ((rc = launch_fused_fwd(f, m, st))) return rc;
+        } else {
+            if ((rc = launch_ae_encoder_fwd(o->iota_rows, d_indptr, d_indices, d_val, W1t, b1, H1, o->a1, m, br, st)))
+                return rc;
+            if ((rc = launch_dense_fwd(o->a1, W2, b2, o->c, nullptr, nodrop, m, H2, H1, 1, br, st))) return rc;
+            if ((rc = launch_dense_fwd(o->c, W3, b3, o->a3, nullptr, nodrop, m, H1, H2, 1, br, st))) return rc;
+        }
         if (o->dec_mode == 1) {
             // rows [lo, hi) of the split: a3 holds them from row 0, the CSR rows are iota_rows[lo + j]
             if ((rc = launch_decoder_tc_fwd(o->iota_rows, t_indptr, t_indices, nullptr, o->a3, W4, b4, H1, o->n_dec,
@@ -1004,7 +1146,10 @@ int dmt_group_train(dmt_group_t* g, const int32_t* const* rows, const int32_t* c
                                          cudaMemcpyDeviceToDevice, g->st));
     // later per-organization work (predict, get_params) must see the trained parameters
     DMT_CUDA(cudaEventRecord(g->ev, g->st));
-    for (int i = 0; i < G; ++i) DMT_CUDA(cudaStreamWaitEvent(g->orgs[i]->st, g->ev, 0));
+    for (int i = 0; i < G; ++i) {
+        DMT_CUDA(cudaStreamWaitEvent(g->orgs[i]->st, g->ev, 0));
+        if ((rc = refresh_shadows(g->orgs[i]))) return rc;  // the group's Adam wrote P
+    }
     return 0;
 }
 

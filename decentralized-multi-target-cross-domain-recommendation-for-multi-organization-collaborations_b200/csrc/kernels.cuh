@@ -152,6 +152,91 @@ int launch_ae_decoder_chunks(const int32_t* rows, const int32_t* indptr, const i
                              const int32_t* n_targets, const int32_t* ent_off, DecChunks dc, float* gout, float* dZ3,
                              float* loss_rows, int n_rows_max, BatchRef br, cudaStream_t st, int blocks_hint = 0);
 
+// ---- fused.cu: the six-launch training step (see the header comment of fused.cu)
+constexpr int kFusedRows = 8;        // batch rows per CTA of the row-local forward / backward kernels
+constexpr int kDbPartStride = 768;   // per row-CTA column-sum partials: db3 [256] | db2 halves [2 x 128] | db1 [256]
+constexpr int kDwSlice = 64;         // batch rows per split of the dW3 / dW2 tiles (<= 8 slices: batch_rows <= 512)
+constexpr int kFusedMaxRowChunks = 4095;  // 12-bit chunk counters in the decoder chunk metadata
+
+struct FusedFwd {
+    BatchRef br;
+    const int32_t *rows, *d_indptr, *d_indices;
+    const float* d_val;
+    const float *W1t, *b1, *W2t, *b2, *W3t, *b3;
+    float *a1, *a2, *c, *a3;  // a1 / a2 / c may be null (prediction)
+    Dropout drop;
+};
+struct FusedDec {
+    BatchRef br;
+    const int4* meta;                // per chunk, plan_dec_meta_kernel
+    const int32_t* batch_chunk_off;  // [nb + 1]
+    const int32_t* n_targets;        // [nb] targets per batch
+    const int32_t* t_indices;
+    const float* target;
+    const int32_t* inv_perm;         // batch-order entry id -> position in the (batch, column)-sorted order
+    const float *A3, *W4, *b4;
+    float *g_sorted, *dZ3, *loss_rows, *dz_part, *loss_part;
+    int* row_cnt;                    // [batch_rows] arrival counters, zero between steps
+};
+struct FusedBwd {
+    BatchRef br;
+    const int32_t* t_len;            // targets per batch-row (epoch-wide index)
+    const float *dz3, *W3, *W2, *a1, *a2;
+    float *dz2, *dz1, *part_db;
+    Dropout drop;
+};
+struct FusedSeg {
+    const int4* meta;                // per chunk: {e0, e1, output row, k | n_chunks << 16}
+    const int32_t* batch_chunk_off;
+    const int32_t* row_sorted;       // in-batch source row of every sorted entry
+    const float* coef_sorted;        // coefficient of every sorted entry
+    float* part;
+    float* part_bias;
+    int* cnt;                        // arrival counters at the first partial slot of a segment, zero between steps
+    const int32_t* active;
+    int b;
+};
+struct FusedGrad {
+    BatchRef br;
+    const int32_t* t_len;
+    const float *dz3, *dz2, *c, *a1;
+    const float* part_db;
+    float* G;
+    int64_t oW2, oW3, ob1, ob2, ob3;
+    float* part_dw;                  // [16 tiles x 8 slices x 64 x 64]
+    int* dw_cnt;                     // [16]
+};
+struct FusedPlanSide {
+    int64_t n_entries;
+    int n_cols;
+    const int32_t *n_seg, *seg_off, *seg_key, *seg_chunk_off, *perm, *ent_row;
+    const float* val_ord;            // null on the target side
+    int4* seg_meta;
+    int32_t* row_sorted;
+    float* val_sorted;               // null on the target side
+    int32_t* inv_perm;               // null on the data side
+};
+struct FusedPlanArgs {
+    int64_t dec_chunk_cap;
+    int n_rows;
+    const int32_t *t_chunk_off, *t_chunk_row, *rows, *row_off, *row_batch, *t_indptr, *t_ent_off;
+    int4* dec_meta;
+    FusedPlanSide t, d;
+};
+int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st);
+int launch_fused_dec(const FusedDec& p, int blocks_hint, cudaStream_t st);
+int launch_fused_bwd_phase(const FusedBwd& p, const FusedSeg& s, const float* src, float* grad, float* bias_grad,
+                           int n_rows_max, int n_chunk_max, cudaStream_t st);
+int launch_fused_grad_phase(const FusedGrad& p, const FusedSeg& s, const float* src, float* grad, int n_chunk_max,
+                            cudaStream_t st);
+int launch_norm_prepare(const float* g, int64_t n, float* partial, int* ticket, AdamScalars* sc, AdamHyper hp,
+                        int* step_dev, const float* loss_rows, const int32_t* t_len, const int32_t* n_targets_ptr,
+                        float* loss_out, BatchRef br, cudaStream_t st);
+int launch_adam_shadow(float* w, float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
+                       int64_t oW2, int64_t oW3, float* W2t, float* W3t, cudaStream_t st);
+int launch_shadow_refresh(const float* W2, const float* W3, float* W2t, float* W3t, cudaStream_t st);
+int launch_plan_fused(const FusedPlanArgs& a, cudaStream_t st);
+
 // ---------------------------------------------------------------- organization groups (one launch = all organizations)
 // Device-visible view of one organization. A group launch adds the organization as grid dimension z, so a step of
 // ALL organizations of a rank is the same ~20 launches as a step of one (the per-organization kernels are far too

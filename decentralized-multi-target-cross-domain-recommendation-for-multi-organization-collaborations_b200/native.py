@@ -82,6 +82,8 @@ def _declare(lib):
         "dmt_org_set_decoder_mode": (I, [P, I, I]),
         "dmt_org_set_fanout": (I, [P, I]),
         "dmt_org_set_decoder_blocks": (I, [P, I]),
+        "dmt_org_set_step_mode": (I, [P, I]),
+        "dmt_org_step_mode": (I, [P]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
         "dmt_ae_decoder_fwd": (I, [P, I, P, P, P, P, P, P, I, I, P, P, P, P, P, I, P]),
         "dmt_eval_blocks": (I, [P, P, P, I, I, I, I, P, P, P]),
@@ -526,6 +528,13 @@ class Org:
     def set_decoder_blocks(self, blocks):
         """Grid of the decoder chunk kernel (0: two blocks per SM); fewer blocks pay with many organizations per GPU."""
         check(self._lib.dmt_org_set_decoder_blocks(self.h, int(blocks)), "dmt_org_set_decoder_blocks")
+
+    def set_step_mode(self, mode):
+        """'fused' (six launches per batch, csrc/fused.cu) or 'classic' (one kernel per layer / reduction)."""
+        check(self._lib.dmt_org_set_step_mode(self.h, {"classic": 0, "fused": 1}[mode]), "dmt_org_set_step_mode")
+
+    def step_mode(self):
+        return "fused" if self._lib.dmt_org_step_mode(self.h) else "classic"
 
     def set_fanout(self, on):
         """Backward pass of a step as parallel graph branches (pays with few organizations per GPU)."""

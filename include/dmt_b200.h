@@ -252,6 +252,14 @@ int dmt_org_set_fanout(dmt_org_t* org, int on);
  * (148), because the kernel's register footprint then leaves room for the other organizations' kernels (measured at
  * ML1M shape, 18 organizations: 214.7 -> 205.6 ms per round while the kernel itself goes from 23.6 to 32.9 us). */
 int dmt_org_set_decoder_blocks(dmt_org_t* org, int blocks);
+/* How one iteration of the batch loop (src/organization.py:149-162) is cut into launches. mode 1 (default whenever
+ * H1 = 256, H2 = 128, batch_rows <= 512 and decoder mode 0): the fused step of csrc/fused.cu — six dependent launches
+ * (row-local forward, decoder chunks, {row-local backward | dW4 segments}, {dW3/dW2 tiles | bias gradients | dW1
+ * segments}, norm + step scalars, Adam), finish passes replaced by last-arriver sums in chunk order. mode 0: the
+ * classic step of twenty kernels (one per layer / reduction). Same arithmetic contract; sums are taken in a different
+ * but fixed order. dmt_org_step_mode returns the mode in effect (0 while the tensor-core decoder is on). */
+int dmt_org_set_step_mode(dmt_org_t* org, int mode);
+int dmt_org_step_mode(const dmt_org_t* org);
 /* number of fp32 parameters; flat layout: W1t[n_enc*H1] b1[H1] W2[H2*H1] b2[H2] W3[H1*H2] b3[H1] W4[n_dec*H1] b4[n_dec] */
 int64_t dmt_org_num_params(const dmt_org_t* org);
 /* Copy parameters in/out (device pointers, flat layout above). set also resets the Adam state: the reference builds

@@ -190,7 +190,7 @@ def chunk_census(T, batches, dec_chunk=128, seg_chunk=64):
 
 
 @pytest.mark.parametrize("mode", ["epoch", "epoch_fanout", "round"])
-@pytest.mark.parametrize("decoder", ["gather", "tc"])
+@pytest.mark.parametrize("decoder", ["gather", "gather_classic", "tc"])
 @pytest.mark.parametrize("shape", ["ml1m_batch", "zipf_wide"])
 def test_train_benchmark_shape(nat, shape, decoder, mode):
     """The paths the benchmark runs (VERDICT r1 'parity hole'): 500-row batches over 3706 target columns with rows of
@@ -224,7 +224,13 @@ def test_train_benchmark_shape(nat, shape, decoder, mode):
     d_csr = (cu(D.indptr, torch.int32), cu(D.indices, torch.int32), cu(D.data))
     t_csr = (cu(T.indptr, torch.int32), cu(T.indices, torch.int32))
     org = nat.Org(n_rows, n_enc, n_dec, 256, 128, d_csr, t_csr, bs, 0, plan_epochs=n_epochs if mode == "round" else 1)
+    # "gather": the fused six-launch step (csrc/fused.cu, the default); "gather_classic": one kernel per layer
+    want_fused = decoder == "gather"
+    if decoder == "gather_classic":
+        org.set_step_mode("classic")
+        decoder = "gather"
     org.set_decoder_mode(decoder)
+    assert org.step_mode() == ("fused" if want_fused else "classic")
     org.set_fanout(mode == "epoch_fanout")
     org.wait_current()
     org.set_params(flat_params(p0).cuda())

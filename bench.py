@@ -37,6 +37,11 @@ WORKLOAD = ("ML1M-shape AAE assist round: 6040x3706, 900188 train / 100021 test 
             "20 local epochs, batch 500 rows")
 METRIC = "MTAL assist-round rating-visits/sec (ML1M-shape AAE, K*(20*nnz_train+nnz_train+nnz_test) per round)"
 UNIT = "rating-visits/s"
+# BASELINE.json configs 3 and 4 (AAE assistance rounds at Douban / Amazon shape; shapes assumed as in SURVEY.md 8d)
+OTHER_CONFIGS = [
+    ("douban", "Douban_user_explicit_ae_0_genre_assist_constant-0.3_constant", "Douban"),
+    ("amazon", "Amazon_user_implicit_ae_0_genre_assist_constant-0.1_optim_0.5_dp-10", "Amazon"),
+]
 
 
 def measured_peaks():
@@ -143,10 +148,10 @@ def cpu_round_sample(mats, data_split, n_orgs_sample=1, epochs_sample=1, batch_r
     return visits, time.perf_counter() - t0
 
 
-def reference_leg(threads, steps, warmup, device="cpu", budget_s=200.0, timeout=900):
+def reference_leg(threads, steps, warmup, device="cpu", budget_s=200.0, timeout=900, control=None, data="ML1M"):
     """Time the UNMODIFIED reference (baseline/_ref/src) in a child process (its global cfg / argparse-at-import do not
     mix with this process): baseline/ref_arm.py. Returns its result dict, or {'unavailable': why}."""
-    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_arm.py"), "--control", CONTROL, "--data", "ML1M",
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_arm.py"), "--control", control or CONTROL, "--data", data,
            "--device", device, "--threads", str(threads), "--steps", str(steps), "--warmup", str(warmup),
            "--budget-s", str(budget_s)]
     try:
@@ -289,6 +294,17 @@ def run_ours(args):
     e2e = run_e2e(args, data, rank, world, dev)
 
     mf = run_mf_joint(data, dev) if (rank == 0 and world == 1) else None
+    # the other BASELINE.json configurations, as extra blocks of the line (N=1 only; each with its own CPU leg)
+    more = None
+    if rank == 0 and world == 1 and args.configs != "none":
+        rounds.close()
+        more = {}
+        for key, control, data_name in OTHER_CONFIGS:
+            if args.configs in ("all", key):
+                try:
+                    more[key] = run_config_block(control, data_name, dev)
+                except Exception as e:  # a failing side block must not take the headline line with it
+                    more[key] = {"control_name": control, "error": "{}: {}".format(type(e).__name__, e)}
     if world > 1:
         D.barrier()
         import torch.distributed as tdist
@@ -322,7 +338,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2: per-round working set (18 x 17 MB parameters+moments, "
                                     "2 x 72 MB prediction matrices, plans) exceeds 126 MB"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
-            "cpu_baseline": cpu, "mf_joint": mf}
+            "cpu_baseline": cpu, "mf_joint": mf, "other_configs": more}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -522,6 +538,81 @@ def run_mf_joint(data, dev, epochs=3):
                              "sample": "one joint-MF epoch with the oracle port ({:.1f} s)".format(cpu_sec)}}
 
 
+
+def run_config_block(control, data_name, dev, n_rounds=2, n_warm=2, local_epochs=20, cpu_leg=True):
+    """One more BASELINE.json configuration as a block of the bench line: device-resident assistance rounds
+    (roundloop.AssistRounds, same code path as `value`) on the synthetic shape SURVEY.md section 8d fixes for it, CUDA-event
+    timed after warm-up; the per-class step profile of one organization; the decoder kernel's algorithmic-byte rate;
+    and the unmodified reference on the host cores for the same control string (bounded sample)."""
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import engine as E
+    from dmtcdr_b200 import roundloop, runner, synth
+    from dmtcdr_b200.config import make_cfg
+
+    cfg = make_cfg(control, device="cuda", seed=0)
+    data = synth.make_rating_data(data_name, seed=0)
+    torch.manual_seed(0)
+    dataset = runner.fetch_dataset(data)
+    runner.process_dataset(dataset)
+    split = [s.numpy() for s in runner.split_dataset(dataset)]
+    mats = {k: (dataset[k].data, dataset[k].target) for k in dataset}
+    a = cfg["assist"]
+    clamp = cfg["data_name"] in ("Douban", "Amazon") and not (
+        cfg["data_name"] == "Douban" and cfg["data_mode"] == "item" and cfg["target_mode"] == "explicit")
+    privacy = (cfg["pl_mode"], cfg["pl_param"]) if cfg.get("pl", "none") != "none" else None
+    bs = cfg["local"]["batch_size"]["train"]
+    R = roundloop.AssistRounds(mats, split, cfg["target_mode"], bs, clamp=clamp, ar=a["ar"], ar_mode=a["ar_mode"],
+                               aw_mode=a["aw_mode"], match_rate=a.get("match_rate", 1.0), local_epochs=local_epochs,
+                               device=dev, privacy=privacy)
+    R.round0()
+    for t in range(1, n_warm + 1):
+        R.run_round(t)
+    R.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {"train_predict": 0.0, "update": 0.0}
+    e0.record()
+    for t in range(n_warm + 1, n_warm + n_rounds + 1):
+        h0 = time.perf_counter()
+        R.train_predict(t)
+        h1 = time.perf_counter()
+        R.combine()
+        phase["train_predict"] += h1 - h0
+        phase["update"] += time.perf_counter() - h1
+    e1.record()
+    R.sync()
+    ms = e0.elapsed_time(e1) / n_rounds
+    visits = R.rating_visits_per_round()
+    eng = R.eng[R.my_orgs[0]]
+    prof = eng.h.profile_step(b=0, reps=20)
+    n_tr = R.state.y["train"].nnz
+    nb = -(-R.n_rows // bs)
+    t_batch = n_tr / nb
+    bytes_dec = t_batch * (4 * 256 + 16) + min(bs, R.n_rows) * 256 * 4 * 2
+    hbm, _ = measured_peaks()
+    metrics = R.evaluate("test")
+    out = {"control_name": control,
+           "workload": "{}-shape (synthetic, SURVEY.md 8d): {} x {}, {} train / {} test entries, {} organizations, "
+                       "batch {} rows, {} local epochs".format(data_name, R.n_rows, R.state.n_cols, n_tr,
+                                                               R.state.y["test"].nnz, R.K, bs, local_epochs),
+           "ms_per_round": ms, "value": visits / (ms / 1e3), "unit": UNIT,
+           "host_ms_per_round": {k: 1e3 * v / n_rounds for k, v in phase.items()},
+           "step_mode": eng.h.step_mode(), "decoder": eng.decoder, "step_kernel_ms": prof,
+           "step_sum_us": 1e3 * sum(prof.values()),
+           "decoder_roofline": {"algorithmic_bytes_per_launch": bytes_dec, "ms_per_launch": prof["decoder_loss_dz3"],
+                                "achieved_GBps": bytes_dec / (prof["decoder_loss_dz3"] * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": bytes_dec / (prof["decoder_loss_dz3"] * 1e-3) / 1e9 / hbm},
+           "test_metrics_after_{}_rounds".format(n_warm + n_rounds): metrics}
+    R.close()
+    del R
+    torch.cuda.empty_cache()
+    if cpu_leg:
+        ref = reference_leg(os.cpu_count() or 1, 2, 1, budget_s=60.0, control=control, data=data_name)
+        out["cpu_baseline"] = ref if "unavailable" in ref else {
+            "value": ref["value"], "unit": UNIT, "cores": ref["cores"], "kind": "reference", "round_s": ref["round_s"],
+            "sample": ref["sample"]}
+    return out
+
+
 def run_e2e(args, data, rank, world, dev):
     """Rounds through the drop-in API (host scipy CSR in / out). Every rank runs the full problem independently when
     world > 1 is not wired into the drop-in classes, so the e2e figure is reported for N=1 semantics on rank 0."""
@@ -566,6 +657,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--local-epochs", dest="local_epochs", type=int, default=20)
+    ap.add_argument("--configs", default="all", help="extra BASELINE configs as blocks of the line: all|none|douban|amazon")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

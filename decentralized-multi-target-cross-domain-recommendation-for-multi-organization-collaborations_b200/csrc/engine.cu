@@ -381,11 +381,22 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
                    o->a3, W4, b4, o->g_sorted, o->dz3, o->loss_rows, o->dz_part, o->loss_part, o->row_cnt};
         if ((rc = launch_fused_dec(d, o->dec_blocks, st))) return rc;
     }
+    // dW4 / db4 only has to be complete before the norm: it runs as a parallel branch of the captured step graph next
+    // to the critical path backward rows -> dW3 / dW2 / dW1 (profiling keeps everything on the main stream)
+    const bool par = only < 0;
+    cudaStream_t sA = par ? o->aux[0] : st;
     if (WANT(K_SEG_W4)) {
-        FusedBwd w{br, o->pt.len, o->dz3, W3, W2, o->a1, o->a2, o->dz2, o->dz1, o->part_db, drop};
+        if (par) {
+            DMT_CUDA(cudaEventRecord(o->fev[0], st));
+            DMT_CUDA(cudaStreamWaitEvent(sA, o->fev[0], 0));
+        }
         FusedSeg s{o->t_seg_meta, o->pt.batch_chunk_off, o->t_row_sorted, o->g_sorted, o->pt.part, o->pt.part_bias,
                    o->t_seg_cnt, o->active, b};
-        if ((rc = launch_fused_bwd_phase(w, s, o->a3, G + o->oW4, G + o->ob4, B, o->n_dec * 2, st))) return rc;
+        if ((rc = launch_fused_seg_chunks(s, o->a3, G + o->oW4, G + o->ob4, o->n_dec * 2, sA))) return rc;
+    }
+    if (WANT(K_SEG_W1)) {
+        FusedBwd w{br, o->pt.len, o->dz3, W3, W2, o->a1, o->a2, o->dz2, o->dz1, o->part_db, drop};
+        if ((rc = launch_fused_bwd_rows(w, B, st))) return rc;
     }
     if (WANT(K_DENSE_BWD)) {
         FusedGrad g{br, o->pt.len, o->dz3, o->dz2, o->c, o->a1, o->part_db, G, o->oW2, o->oW3, o->ob1, o->ob2, o->ob3,
@@ -394,12 +405,17 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
                    o->d_seg_cnt, o->active, b};
         if ((rc = launch_fused_grad_phase(g, s, o->dz1, G + o->oW1, o->n_enc * 2, st))) return rc;
     }
+    if (par) {  // join
+        DMT_CUDA(cudaEventRecord(o->fev[1], sA));
+        DMT_CUDA(cudaStreamWaitEvent(st, o->fev[1], 0));
+    }
     if (WANT(K_NORM))
-        if ((rc = launch_norm_prepare(G, o->n_params, o->partial, o->norm_ticket, o->sc, hp, o->step_dev, o->loss_rows,
-                                      o->pt.len, o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
+        if ((rc = launch_norm_prepare(G, o->n_params, o->partial, o->sc, o->step_dev, o->loss_rows, o->pt.len,
+                                      o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
             return rc;
     if (WANT(K_ADAM))
-        if ((rc = launch_adam_shadow(o->P, G, o->M, o->V, o->n_params, o->sc, hp, o->oW2, o->oW3, o->W2t, o->W3t, st)))
+        if ((rc = launch_adam_shadow(o->P, G, o->M, o->V, o->n_params, o->sc, hp, o->partial, o->step_dev, o->oW2,
+                                     o->oW3, o->W2t, o->W3t, st)))
             return rc;
 #undef WANT
     return 0;

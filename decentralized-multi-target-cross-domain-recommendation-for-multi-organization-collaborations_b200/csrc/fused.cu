@@ -8,9 +8,10 @@
 //   2 ae_dec_chunks    decoder SDDMM + loss + g = dL/do + partial dZ3 per chunk of <= 128 targets of one row; the LAST
 //                      chunk of a row to arrive adds the row's partials in chunk order (deterministic) and applies the
 //                      tanh derivative -> no finish kernel. g is scattered straight into (batch, column)-sorted order.
-//   3 ae_bwd_phase     two block roles in one launch: (a) row-local backward dZ3 -> dZ2 -> dZ1 with per-CTA column-sum
-//                      partials for db3 / db2 / db1, (b) dW4 / db4 as a chunked segmented reduction over the sorted
-//                      targets (last-arriving chunk of a multi-chunk segment adds the partial rows in order).
+//   3 ae_bwd_rows      row-local backward dZ3 -> dZ2 -> dZ1 with per-CTA column-sum partials for db3 / db2 / db1;
+//     ae_seg_chunks    on a PARALLEL branch of the step graph (it only has to finish before the norm): dW4 / db4 as a
+//                      chunked segmented reduction over the sorted targets (last-arriving chunk of a multi-chunk
+//                      segment adds the partial rows in order).
 //   4 ae_grad_phase    three block roles: (a) dW3 = dZ3^T C and dW2 = dZ2^T A1 as 64x64 FFMA tiles, split over row
 //                      slices, last slice to arrive adds the slices in order, (b) bias-gradient finish, (c) dW1t as a
 //                      chunked segmented reduction over the sorted data entries.
@@ -41,6 +42,39 @@ __device__ __forceinline__ void add4(float4& acc, const float4& x) {
 }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+
+
+// acc[i] += sum_k act[row0 + i][k] * W[k * ld + col] for k < K: the weight column is streamed from L2 in batches of
+// PF values per thread, the next batch in flight while the current one is consumed (these row-local kernels run few
+// CTAs, so memory-level parallelism has to come from each thread); the activations are broadcast from shared memory.
+template <int NR, int K, int PF, int LDA>
+__device__ __forceinline__ void stream_matvec(float (&acc)[NR], const float* __restrict__ w, int ld,
+                                              const float (*act)[LDA], int row0) {
+    static_assert(K % PF == 0 && PF % 4 == 0, "prefetch batch");
+    float cur[PF], nxt[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) cur[i] = w[(int64_t)i * ld];
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += PF) {
+        if (k0 + PF < K) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) nxt[i] = w[(int64_t)(k0 + PF + i) * ld];
+        }
+#pragma unroll
+        for (int q = 0; q < PF / 4; ++q) {
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(&act[row0 + i][k0 + 4 * q]);
+                acc[i] = fmaf(a.x, cur[4 * q + 0], acc[i]);
+                acc[i] = fmaf(a.y, cur[4 * q + 1], acc[i]);
+                acc[i] = fmaf(a.z, cur[4 * q + 2], acc[i]);
+                acc[i] = fmaf(a.w, cur[4 * q + 3], acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PF; ++i) cur[i] = nxt[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ 1 forward rows
@@ -111,20 +145,7 @@ __device__ __forceinline__ void fwd_rows_body(const FusedFwd& p, int cta) {
         const float bias = p.b2[n];
 #pragma unroll
         for (int i = 0; i < RH; ++i) acc[i] = bias;
-        const float* w = p.W2t + n;
-#pragma unroll 4
-        for (int k4 = 0; k4 < H1c / 4; ++k4) {
-            const float w0 = w[(4 * k4 + 0) * H2c], w1 = w[(4 * k4 + 1) * H2c], w2 = w[(4 * k4 + 2) * H2c],
-                        w3 = w[(4 * k4 + 3) * H2c];
-#pragma unroll
-            for (int i = 0; i < RH; ++i) {
-                const float4 a = *reinterpret_cast<const float4*>(&a1s[g * RH + i][4 * k4]);
-                acc[i] = fmaf(a.x, w0, acc[i]);
-                acc[i] = fmaf(a.y, w1, acc[i]);
-                acc[i] = fmaf(a.z, w2, acc[i]);
-                acc[i] = fmaf(a.w, w3, acc[i]);
-            }
-        }
+        stream_matvec<RH, H1c, 32, H1c>(acc, p.W2t + n, H2c, a1s, g * RH);
 #pragma unroll
         for (int i = 0; i < RH; ++i) {
             const int row = g * RH + i;
@@ -147,20 +168,7 @@ __device__ __forceinline__ void fwd_rows_body(const FusedFwd& p, int cta) {
         const float bias = p.b3[n];
 #pragma unroll
         for (int i = 0; i < R; ++i) acc[i] = bias;
-        const float* w = p.W3t + n;
-#pragma unroll 4
-        for (int k4 = 0; k4 < H2c / 4; ++k4) {
-            const float w0 = w[(4 * k4 + 0) * H1c], w1 = w[(4 * k4 + 1) * H1c], w2 = w[(4 * k4 + 2) * H1c],
-                        w3 = w[(4 * k4 + 3) * H1c];
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const float4 a = *reinterpret_cast<const float4*>(&cs[i][4 * k4]);
-                acc[i] = fmaf(a.x, w0, acc[i]);
-                acc[i] = fmaf(a.y, w1, acc[i]);
-                acc[i] = fmaf(a.z, w2, acc[i]);
-                acc[i] = fmaf(a.w, w3, acc[i]);
-            }
-        }
+        stream_matvec<R, H2c, 32, H2c>(acc, p.W3t + n, H1c, cs, 0);
 #pragma unroll
         for (int i = 0; i < R; ++i)
             if (r0 + i < m) p.a3[(int64_t)(r0 + i) * H1c + n] = tanhf(acc[i]);
@@ -329,20 +337,7 @@ __device__ __forceinline__ void bwd_rows_body(const FusedBwd& p, int cta) {
         float acc[RH];
 #pragma unroll
         for (int i = 0; i < RH; ++i) acc[i] = 0.f;
-        const float* w = p.W3 + k;
-#pragma unroll 4
-        for (int n4 = 0; n4 < H1c / 4; ++n4) {
-            const float w0 = w[(4 * n4 + 0) * H2c], w1 = w[(4 * n4 + 1) * H2c], w2 = w[(4 * n4 + 2) * H2c],
-                        w3 = w[(4 * n4 + 3) * H2c];
-#pragma unroll
-            for (int i = 0; i < RH; ++i) {
-                const float4 d = *reinterpret_cast<const float4*>(&d3s[g * RH + i][4 * n4]);
-                acc[i] = fmaf(d.x, w0, acc[i]);
-                acc[i] = fmaf(d.y, w1, acc[i]);
-                acc[i] = fmaf(d.z, w2, acc[i]);
-                acc[i] = fmaf(d.w, w3, acc[i]);
-            }
-        }
+        stream_matvec<RH, H1c, 32, H1c>(acc, p.W3 + k, H2c, d3s, g * RH);
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < RH; ++i) {
@@ -367,20 +362,7 @@ __device__ __forceinline__ void bwd_rows_body(const FusedBwd& p, int cta) {
         float acc[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) acc[i] = 0.f;
-        const float* w = p.W2 + k;
-#pragma unroll 4
-        for (int n4 = 0; n4 < H2c / 4; ++n4) {
-            const float w0 = w[(4 * n4 + 0) * H1c], w1 = w[(4 * n4 + 1) * H1c], w2 = w[(4 * n4 + 2) * H1c],
-                        w3 = w[(4 * n4 + 3) * H1c];
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const float4 d = *reinterpret_cast<const float4*>(&d2s[i][4 * n4]);
-                acc[i] = fmaf(d.x, w0, acc[i]);
-                acc[i] = fmaf(d.y, w1, acc[i]);
-                acc[i] = fmaf(d.z, w2, acc[i]);
-                acc[i] = fmaf(d.w, w3, acc[i]);
-            }
-        }
+        stream_matvec<R, H2c, 32, H2c>(acc, p.W2 + k, H1c, d2s, 0);
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < R; ++i) {
@@ -579,15 +561,14 @@ __global__ void __launch_bounds__(256) ae_fwd_rows_kernel(FusedFwd p) { fwd_rows
 
 __global__ void __launch_bounds__(256) ae_dec_chunks_kernel(FusedDec p) { dec_chunks_body(p); }
 
-__global__ void __launch_bounds__(256) ae_bwd_phase_kernel(FusedBwd p, FusedSeg s, const float* src, float* grad,
-                                                           float* bias_grad, int n_row_ctas) {
-    if ((int)blockIdx.x < n_row_ctas) {
-        bwd_rows_body<kFusedRows>(p, blockIdx.x);
-        return;
-    }
+// 3a and 3b are separate kernels on parallel branches of the step graph: the row kernel keeps 64 weights per thread in
+// flight (~100 registers), the segment kernel needs 64 registers and four resident blocks per SM.
+__global__ void __launch_bounds__(256) ae_bwd_rows_kernel(FusedBwd p) { bwd_rows_body<kFusedRows>(p, blockIdx.x); }
+
+__global__ void __launch_bounds__(256) ae_seg_chunks_kernel(FusedSeg s, const float* src, float* grad,
+                                                            float* bias_grad) {
     if (s.active != nullptr && s.active[s.b] == 0) return;
-    const int blk = blockIdx.x - n_row_ctas;
-    seg_chunks_body(s, src, grad, bias_grad, blk * 8 + (threadIdx.x >> 5), (gridDim.x - n_row_ctas) * 8);
+    seg_chunks_body(s, src, grad, bias_grad, blockIdx.x * 8 + (threadIdx.x >> 5), gridDim.x * 8);
 }
 
 __global__ void __launch_bounds__(256) ae_grad_phase_kernel(FusedGrad p, FusedSeg s, const float* src, float* grad) {
@@ -604,17 +585,22 @@ __global__ void __launch_bounds__(256) ae_grad_phase_kernel(FusedGrad p, FusedSe
     seg_chunks_body(s, src, grad, nullptr, (blk - 129) * 8 + (threadIdx.x >> 5), (gridDim.x - 129) * 8);
 }
 
-// 5: sum of squares of the gradient; the last block finishes what adam_prepare used to do in its own launch
+// 5: sum of squares of the gradient, one partial per block (no tail: the Adam blocks add the partials themselves).
+// Block 0 also advances the step counter (every reader of the old value — the dropout draws of this step — ran in
+// earlier launches), block 1 reduces the batch loss.
 __global__ void __launch_bounds__(256) norm_prepare_kernel(const float* __restrict__ g, int64_t n, float* partial,
-                                                           int* ticket, AdamScalars* sc, AdamHyper hp, int* step_dev,
-                                                           const float* loss_rows, const int32_t* t_len,
-                                                           const int32_t* n_targets_ptr, float* loss_out, BatchRef br) {
+                                                           AdamScalars* sc, int* step_dev, const float* loss_rows,
+                                                           const int32_t* t_len, const int32_t* n_targets_ptr,
+                                                           float* loss_out, BatchRef br) {
     __shared__ float sh[32];
-    __shared__ int s_last;
     int lo, hi;
     if (!batch_range(br, lo, hi)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->active = 0;
         return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *step_dev += 1;
+        sc->active = 1;
     }
     float s = 0.f;
     const int64_t n4 = n >> 2;
@@ -625,45 +611,45 @@ __global__ void __launch_bounds__(256) norm_prepare_kernel(const float* __restri
     }
     for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s += g[i] * g[i];
     s = block_sum(s, sh);
-    if (threadIdx.x == 0) {
-        partial[blockIdx.x] = s;
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    float tot = 0.f;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) tot += __ldcg(partial + i);
-    tot = block_sum(tot, sh);
-    float l = 0.f;
-    for (int i = threadIdx.x; i < hi - lo; i += blockDim.x)
-        if (t_len[lo + i] > 0) l += loss_rows[i];
-    l = block_sum(l, sh);
-    if (threadIdx.x == 0) {
-        *step_dev += 1;
-        const int64_t t = *step_dev;
-        float coef = 1.f;
-        if (hp.max_norm > 0.f) coef = fminf(1.f, hp.max_norm / (sqrtf(tot) + 1e-6f));
-        const double bc1 = 1.0 - pow(hp.beta1, (double)t);
-        const double bc2 = 1.0 - pow(hp.beta2, (double)t);
-        sc->coef = coef;
-        sc->step_size = (float)(hp.lr / bc1);
-        sc->bc2_sqrt = (float)sqrt(bc2);
-        sc->active = 1;
-        if (loss_out != nullptr) loss_out[0] = l / (float)n_targets_ptr[0];
-        *ticket = 0;
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    if (blockIdx.x == 1 % gridDim.x && loss_out != nullptr) {
+        float l = 0.f;
+        for (int i = threadIdx.x; i < hi - lo; i += blockDim.x)
+            if (t_len[lo + i] > 0) l += loss_rows[i];
+        l = block_sum(l, sh);
+        if (threadIdx.x == 0) loss_out[0] = l / (float)n_targets_ptr[0];
     }
 }
 
-// 6: dense Adam(+L2) with the clip coefficient; also writes the transposed shadows of W2 / W3 it just updated
+// 6: dense Adam(+L2). Every block first adds the norm partials in a fixed order (same value in every block), derives
+// the clip coefficient and the bias corrections from the step counter, then updates its slice; it also writes the
+// transposed shadows of the W2 / W3 elements it updates.
 __global__ void __launch_bounds__(256) adam_shadow_kernel(float* __restrict__ w, float* __restrict__ g,
                                                           float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                           const AdamScalars* __restrict__ sc, AdamHyper hp,
-                                                          int64_t oW2, int64_t oW3, float* __restrict__ W2t,
-                                                          float* __restrict__ W3t) {
+                                                          const float* __restrict__ partial, int n_partial,
+                                                          const int* __restrict__ step_dev, int64_t oW2, int64_t oW3,
+                                                          float* __restrict__ W2t, float* __restrict__ W3t) {
+    __shared__ float sh[32];
+    __shared__ float s_sc[3];
     if (sc->active == 0) return;
-    const float coef = sc->coef, step_size = sc->step_size, bc2_sqrt = sc->bc2_sqrt;
+    {
+        float tot = 0.f;
+        for (int i = threadIdx.x; i < n_partial; i += blockDim.x) tot += partial[i];
+        tot = block_sum(tot, sh);
+        if (threadIdx.x == 0) {
+            const int64_t t = *step_dev;
+            float coef = 1.f;
+            if (hp.max_norm > 0.f) coef = fminf(1.f, hp.max_norm / (sqrtf(tot) + 1e-6f));
+            const double bc1 = 1.0 - pow(hp.beta1, (double)t);
+            const double bc2 = 1.0 - pow(hp.beta2, (double)t);
+            s_sc[0] = coef;
+            s_sc[1] = (float)(hp.lr / bc1);
+            s_sc[2] = (float)sqrt(bc2);
+        }
+        __syncthreads();
+    }
+    const float coef = s_sc[0], step_size = s_sc[1], bc2_sqrt = s_sc[2];
     const float b2 = (float)hp.beta2, eps = (float)hp.eps, wd = (float)hp.weight_decay;
     const float omb1 = (float)(1.0 - hp.beta1), omb2 = (float)(1.0 - hp.beta2);
     const int64_t n4 = n >> 2;
@@ -783,13 +769,19 @@ int launch_fused_dec(const FusedDec& p, int blocks_hint, cudaStream_t st) {
     return 0;
 }
 
-int launch_fused_bwd_phase(const FusedBwd& p, const FusedSeg& s, const float* src, float* grad, float* bias_grad,
-                           int n_rows_max, int n_chunk_max, cudaStream_t st) {
-    const int n_row_ctas = (n_rows_max + kFusedRows - 1) / kFusedRows;
+int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st) {
+    if (n_rows_max <= 0) return 0;
+    ae_bwd_rows_kernel<<<(n_rows_max + kFusedRows - 1) / kFusedRows, 256, 0, st>>>(p);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, float* bias_grad, int n_chunk_max,
+                            cudaStream_t st) {
     int seg_blocks = (n_chunk_max + 7) / 8;
     if (seg_blocks > kNumSMs * 2) seg_blocks = kNumSMs * 2;
     if (seg_blocks < 1) seg_blocks = 1;
-    ae_bwd_phase_kernel<<<n_row_ctas + seg_blocks, 256, 0, st>>>(p, s, src, grad, bias_grad, n_row_ctas);
+    ae_seg_chunks_kernel<<<seg_blocks, 256, 0, st>>>(s, src, grad, bias_grad);
     DMT_LAUNCH_CHECK();
     return 0;
 }
@@ -804,21 +796,23 @@ int launch_fused_grad_phase(const FusedGrad& p, const FusedSeg& s, const float* 
     return 0;
 }
 
-int launch_norm_prepare(const float* g, int64_t n, float* partial, int* ticket, AdamScalars* sc, AdamHyper hp,
-                        int* step_dev, const float* loss_rows, const int32_t* t_len, const int32_t* n_targets_ptr,
-                        float* loss_out, BatchRef br, cudaStream_t st) {
-    norm_prepare_kernel<<<kNormBlocks, 256, 0, st>>>(g, n, partial, ticket, sc, hp, step_dev, loss_rows, t_len,
-                                                     n_targets_ptr, loss_out, br);
+int launch_norm_prepare(const float* g, int64_t n, float* partial, AdamScalars* sc, int* step_dev,
+                        const float* loss_rows, const int32_t* t_len, const int32_t* n_targets_ptr, float* loss_out,
+                        BatchRef br, cudaStream_t st) {
+    norm_prepare_kernel<<<kNormBlocks, 256, 0, st>>>(g, n, partial, sc, step_dev, loss_rows, t_len, n_targets_ptr,
+                                                     loss_out, br);
     DMT_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_adam_shadow(float* w, float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
-                       int64_t oW2, int64_t oW3, float* W2t, float* W3t, cudaStream_t st) {
+                       const float* partial, const int* step_dev, int64_t oW2, int64_t oW3, float* W2t, float* W3t,
+                       cudaStream_t st) {
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;
-    adam_shadow_kernel<<<(int)blocks, 256, 0, st>>>(w, g, m, v, n, sc, hp, oW2, oW3, W2t, W3t);
+    adam_shadow_kernel<<<(int)blocks, 256, 0, st>>>(w, g, m, v, n, sc, hp, partial, kNormBlocks, step_dev, oW2, oW3,
+                                                    W2t, W3t);
     DMT_LAUNCH_CHECK();
     return 0;
 }

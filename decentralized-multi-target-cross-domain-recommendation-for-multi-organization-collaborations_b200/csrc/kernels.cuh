@@ -225,15 +225,17 @@ struct FusedPlanArgs {
 };
 int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st);
 int launch_fused_dec(const FusedDec& p, int blocks_hint, cudaStream_t st);
-int launch_fused_bwd_phase(const FusedBwd& p, const FusedSeg& s, const float* src, float* grad, float* bias_grad,
-                           int n_rows_max, int n_chunk_max, cudaStream_t st);
+int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st);
+int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, float* bias_grad, int n_chunk_max,
+                            cudaStream_t st);
 int launch_fused_grad_phase(const FusedGrad& p, const FusedSeg& s, const float* src, float* grad, int n_chunk_max,
                             cudaStream_t st);
-int launch_norm_prepare(const float* g, int64_t n, float* partial, int* ticket, AdamScalars* sc, AdamHyper hp,
-                        int* step_dev, const float* loss_rows, const int32_t* t_len, const int32_t* n_targets_ptr,
-                        float* loss_out, BatchRef br, cudaStream_t st);
+int launch_norm_prepare(const float* g, int64_t n, float* partial, AdamScalars* sc, int* step_dev,
+                        const float* loss_rows, const int32_t* t_len, const int32_t* n_targets_ptr, float* loss_out,
+                        BatchRef br, cudaStream_t st);
 int launch_adam_shadow(float* w, float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
-                       int64_t oW2, int64_t oW3, float* W2t, float* W3t, cudaStream_t st);
+                       const float* partial, const int* step_dev, int64_t oW2, int64_t oW3, float* W2t, float* W3t,
+                       cudaStream_t st);
 int launch_shadow_refresh(const float* W2, const float* W3, float* W2t, float* W3t, cudaStream_t st);
 int launch_plan_fused(const FusedPlanArgs& a, cudaStream_t st);
 

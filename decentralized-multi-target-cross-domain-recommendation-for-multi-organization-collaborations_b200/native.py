@@ -584,7 +584,13 @@ class Org:
         n = self._lib.dmt_org_profile_classes()
         buf = (C.c_float * n)()
         check(self._lib.dmt_org_profile_step(self.h, int(b), int(reps), buf), "dmt_org_profile_step")
-        return dict(zip(self.PROFILE_CLASSES, [float(x) for x in buf]))
+        vals = [float(x) for x in buf]
+        if self.step_mode() == "fused":  # six launches (+ the dW4 branch): csrc/fused.cu
+            names = {"encoder_spmm": "fwd_rows", "decoder_loss_dz3": "decoder_loss_dz3", "dw4_segments": "dw4_segments",
+                     "dw1_segments": "bwd_rows", "dense_bwd": "grad_phase", "grad_norm": "grad_norm",
+                     "clip_adam": "clip_adam"}
+            return {names[k]: v for k, v in zip(self.PROFILE_CLASSES, vals) if k in names}
+        return dict(zip(self.PROFILE_CLASSES, vals))
 
     def cuda_stream(self):
         return self._lib.dmt_org_stream(self.h)

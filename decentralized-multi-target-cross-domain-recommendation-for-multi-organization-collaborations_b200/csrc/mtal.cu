@@ -44,16 +44,25 @@ __global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------- combine (reference src/assist.py:131-176)
-// One pass over the global CSR for all owners. S (K x K softmax rows) is staged in shared memory.
-template <int KMAX>
+// One pass over the global CSR for all owners. S (K x K softmax rows) is staged in shared memory; with cold start
+// (S_cold != NULL) a second K x K matrix holds softmax(w[1:]) per owner (slot 0 = 0): it is applied wherever
+// organization 0's output is NaN, i.e. for the aligned rows organization 0 never saw (src/models/assist.py:28-34).
+// org_row (may be NULL = identity) maps an organization id to its row of O (rank-blocked layouts, dist.py).
 __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ F_old, const float* __restrict__ O,
                                                       const int32_t* __restrict__ col,
                                                       const int32_t* __restrict__ owner,
                                                       const float* __restrict__ rate_col, const float* __restrict__ S,
                                                       const int64_t* __restrict__ match_end, float* __restrict__ F_new,
-                                                      int64_t nnz, int K) {
-    extern __shared__ float sS[];  // K*K
-    for (int i = threadIdx.x; i < K * K; i += blockDim.x) sS[i] = S[i];
+                                                      int64_t nnz, int K, const int32_t* __restrict__ org_row,
+                                                      const float* __restrict__ S_cold) {
+    extern __shared__ float sS[];  // K*K (+ K*K cold) + K row ids
+    float* sC = sS + K * K;
+    int* sRow = reinterpret_cast<int*>(sS + (S_cold ? 2 : 1) * K * K);
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+        sS[i] = S[i];
+        if (S_cold) sC[i] = S_cold[i];
+    }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sRow[i] = org_row ? org_row[i] : i;
     __syncthreads();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
@@ -62,11 +71,18 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
         const float* s = sS + ow * K;
         float q = 0.f;
         if (match_end == nullptr || p < match_end[ow]) {
+            float o0 = O[(int64_t)sRow[0] * nnz + p];
+            if (S_cold != nullptr && isnan(o0)) {
+                const float* sc = sC + ow * K;
+                for (int j = 1; j < K; ++j) q += O[(int64_t)sRow[j] * nnz + p] * sc[j];
+            } else {
+                q = o0 * s[0];
 #pragma unroll 4
-            for (int j = 0; j < K; ++j) q += O[(int64_t)j * nnz + p] * s[j];
+                for (int j = 1; j < K; ++j) q += O[(int64_t)sRow[j] * nnz + p] * s[j];
+            }
         } else {
             // unmatched entry: the owner's own output fills every slot (reference src/assist.py:98-103)
-            float own = O[(int64_t)ow * nnz + p];
+            float own = O[(int64_t)sRow[ow] * nnz + p];
             for (int j = 0; j < K; ++j) q += own * s[j];
         }
         F_new[p] = F_old[p] + rate_col[c] * q;
@@ -77,15 +93,150 @@ __global__ void __launch_bounds__(256) gather_view_kernel(const float* __restric
                                                           const float* __restrict__ O, const int32_t* __restrict__ pos,
                                                           const int32_t* __restrict__ rank, int64_t nnz, int64_t n,
                                                           int K, int owner, int64_t n_match, float* __restrict__ h,
-                                                          float* __restrict__ t, float* __restrict__ V) {
+                                                          float* __restrict__ t, float* __restrict__ V,
+                                                          const int32_t* __restrict__ org_row) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         int64_t p = pos[e];
         h[e] = F_old[p];
         t[e] = y[p];
         bool matched = rank[e] < n_match;
-        float own = O[(int64_t)owner * nnz + p];
-        for (int j = 0; j < K; ++j) V[(int64_t)j * n + e] = matched ? O[(int64_t)j * nnz + p] : own;
+        float own = O[(int64_t)(org_row ? org_row[owner] : owner) * nnz + p];
+        for (int j = 0; j < K; ++j)
+            V[(int64_t)j * n + e] = matched ? O[(int64_t)(org_row ? org_row[j] : j) * nnz + p] : own;
+    }
+}
+
+// ---------------------------------------------------------------- models.Assist as a differentiable module
+// forward of src/models/assist.py:25-37 over n entries: out is [n x K] addressed as out[e*se + j*sj] (so both the
+// reference's row-major [n, K] stack and an organization-major [K, n] view fit); entries whose slot 0 is NaN (cold
+// start) combine slots 1.. with softmax(w[1:]). q[e] keeps the weighted sum for the backward pass.
+constexpr int kRowsKMax = 64;
+
+__device__ __forceinline__ void softmax_pair(const float* __restrict__ w, int K, float* s, float* sc) {
+    float mx = -INFINITY, mc = -INFINITY;
+    for (int j = 0; j < K; ++j) {
+        mx = fmaxf(mx, w[j]);
+        if (j) mc = fmaxf(mc, w[j]);
+    }
+    float z = 0.f, zc = 0.f;
+    for (int j = 0; j < K; ++j) {
+        s[j] = expf(w[j] - mx);
+        z += s[j];
+        sc[j] = j ? expf(w[j] - mc) : 0.f;
+        zc += sc[j];
+    }
+    for (int j = 0; j < K; ++j) {
+        s[j] /= z;
+        if (j) sc[j] /= zc;
+    }
+}
+
+__global__ void __launch_bounds__(256) assist_rows_fwd_kernel(const float* __restrict__ out, int64_t se, int64_t sj,
+                                                              const float* __restrict__ h,
+                                                              const int32_t* __restrict__ idx,
+                                                              const float* __restrict__ rate,
+                                                              const float* __restrict__ w, int64_t n, int K,
+                                                              float* __restrict__ tgt, float* __restrict__ q_out) {
+    __shared__ float s[kRowsKMax], sc[kRowsKMax];
+    if (threadIdx.x == 0) softmax_pair(w, K, s, sc);
+    __syncthreads();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const float* o = out + e * se;
+        float o0 = o[0], q = 0.f;
+        if (isnan(o0)) {
+            for (int j = 1; j < K; ++j) q += o[j * sj] * sc[j];
+        } else {
+            q = o0 * s[0];
+            for (int j = 1; j < K; ++j) q += o[j * sj] * s[j];
+        }
+        tgt[e] = h[e] + rate[idx[e]] * q;
+        if (q_out) q_out[e] = q;
+    }
+}
+
+// d_rate[seg_key[s]] = sum over the segment's entries of delta*q (entries sorted by idx: perm / seg_* of
+// dmt_sort_segments); one warp per segment, lanes summed in a fixed order -> reproducible.
+__global__ void __launch_bounds__(256) assist_rows_rate_grad_kernel(const int32_t* __restrict__ perm,
+                                                                    const int32_t* __restrict__ seg_key,
+                                                                    const int32_t* __restrict__ seg_off,
+                                                                    const int32_t* __restrict__ n_seg,
+                                                                    const float* __restrict__ delta,
+                                                                    const float* __restrict__ q,
+                                                                    float* __restrict__ d_rate) {
+    int lane = threadIdx.x & 31;
+    int warps = gridDim.x * (blockDim.x >> 5);
+    int ns = n_seg[0];
+    for (int sgm = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sgm < ns; sgm += warps) {
+        int e0 = seg_off[sgm], e1 = seg_off[sgm + 1];
+        float acc = 0.f;
+        for (int e = e0 + lane; e < e1; e += 32) {
+            int src = perm[e];
+            acc += delta[src] * q[src];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) d_rate[seg_key[sgm]] = acc;
+    }
+}
+
+// block partials of d_s (warm entries) and d_sc (cold entries): scratch[b][2K]
+__global__ void __launch_bounds__(256) assist_rows_w_grad_kernel(const float* __restrict__ out, int64_t se, int64_t sj,
+                                                                 const int32_t* __restrict__ idx,
+                                                                 const float* __restrict__ rate,
+                                                                 const float* __restrict__ delta, int64_t n, int K,
+                                                                 float* __restrict__ scratch) {
+    __shared__ float sh[32];
+    __shared__ float s_acc[8][2 * kRowsKMax];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int j = lane; j < 2 * K; j += 32) s_acc[wid][j] = 0.f;
+    __syncwarp();
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t n_round = (n + stride - 1) / stride * stride;  // warp-uniform trip count (shuffles need all lanes)
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_round; e += stride) {
+        bool ok = e < n;
+        const float* o = out + (ok ? e : 0) * se;
+        float o0 = ok ? o[0] : 0.f;
+        float de = ok ? delta[e] * rate[idx[e]] : 0.f;
+        bool cold = isnan(o0);
+        for (int j = 0; j < K; ++j) {
+            float v = (j == 0) ? o0 : (ok ? o[j * sj] : 0.f);
+            float warm = (!cold) ? de * v : 0.f;
+            float cld = (cold && j > 0) ? de * v : 0.f;
+            warm = warp_sum(warm);
+            cld = warp_sum(cld);
+            if (lane == 0) {
+                s_acc[wid][j] += warm;
+                s_acc[wid][K + j] += cld;
+            }
+        }
+    }
+    __syncthreads();
+    (void)sh;
+    for (int j = threadIdx.x; j < 2 * K; j += blockDim.x) {
+        float v = 0.f;
+        for (int i = 0; i < 8; ++i) v += s_acc[i][j];
+        scratch[(int64_t)blockIdx.x * 2 * K + j] = v;
+    }
+}
+
+__global__ void assist_rows_w_finish_kernel(const float* __restrict__ scratch, const float* __restrict__ w, int K,
+                                            int nb, float* __restrict__ d_w) {
+    __shared__ float s[kRowsKMax], sc[kRowsKMax], ds[2 * kRowsKMax];
+    for (int j = threadIdx.x; j < 2 * K; j += blockDim.x) {
+        float v = 0.f;
+        for (int i = 0; i < nb; ++i) v += scratch[(int64_t)i * 2 * K + j];
+        ds[j] = v;
+    }
+    if (threadIdx.x == 0) softmax_pair(w, K, s, sc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float dot = 0.f, dotc = 0.f;
+        for (int j = 0; j < K; ++j) {
+            dot += s[j] * ds[j];
+            dotc += sc[j] * ds[K + j];
+        }
+        for (int j = 0; j < K; ++j) d_w[j] = s[j] * (ds[j] - dot) + sc[j] * (ds[K + j] - dotc);
     }
 }
 
@@ -280,23 +431,65 @@ int dmt_residual(const float* F, const float* y, float* r, int64_t n, int loss_k
 
 int dmt_assist_combine(const float* F_old, const float* O, const int32_t* col, const int32_t* owner,
                        const float* rate_col, const float* S, const int64_t* match_end, float* F_new, int64_t nnz,
-                       int K, void* stream) {
+                       int K, const int32_t* org_row, const float* S_cold, void* stream) {
     DMT_REQUIRE(nnz >= 0 && K >= 1 && K <= 128, "dmt_assist_combine: need 1 <= K <= 128");
     if (nnz == 0) return 0;
-    combine_kernel<128><<<stream_grid(nnz, 2), 256, K * K * sizeof(float), as_stream(stream)>>>(
-        F_old, O, col, owner, rate_col, S, match_end, F_new, nnz, K);
+    size_t smem = ((S_cold ? 2 : 1) * (size_t)K * K + K) * sizeof(float);
+    if (smem > 48 * 1024) {
+        DMT_REQUIRE(smem <= 200 * 1024, "dmt_assist_combine: K too large for the shared-memory weight tables");
+        DMT_CUDA(cudaFuncSetAttribute(combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    combine_kernel<<<stream_grid(nnz, 2), 256, smem, as_stream(stream)>>>(F_old, O, col, owner, rate_col, S, match_end,
+                                                                          F_new, nnz, K, org_row, S_cold);
     DMT_LAUNCH_CHECK();
     return 0;
 }
 
 int dmt_assist_gather_view(const float* F_old, const float* y, const float* O, const int32_t* pos,
                            const int32_t* rank, int64_t nnz, int64_t n, int K, int owner, int64_t n_match, float* h,
-                           float* t, float* V, void* stream) {
+                           float* t, float* V, const int32_t* org_row, void* stream) {
     DMT_REQUIRE(n >= 0 && K >= 1 && owner >= 0 && owner < K, "dmt_assist_gather_view: bad argument");
     if (n == 0) return 0;
     gather_view_kernel<<<stream_grid(n, 1), 256, 0, as_stream(stream)>>>(F_old, y, O, pos, rank, nnz, n, K, owner,
-                                                                         n_match, h, t, V);
+                                                                         n_match, h, t, V, org_row);
     DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int dmt_assist_rows_fwd(const float* out, int64_t stride_e, int64_t stride_j, const float* history, const int32_t* idx,
+                        const float* rate, const float* w, int64_t n, int K, float* target, float* q, void* stream) {
+    DMT_REQUIRE(n >= 0 && K >= 1 && K <= kRowsKMax, "dmt_assist_rows_fwd: need 1 <= K <= 64");
+    if (n == 0) return 0;
+    assist_rows_fwd_kernel<<<stream_grid(n, 2), 256, 0, as_stream(stream)>>>(out, stride_e, stride_j, history, idx, rate,
+                                                                             w, n, K, target, q);
+    DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t dmt_assist_rows_scratch_floats(int K) { return (int64_t)kAssistBlocks * 2 * K; }
+
+int dmt_assist_rows_bwd(const float* out, int64_t stride_e, int64_t stride_j, const int32_t* idx, const float* rate,
+                        const float* w, const float* q, const float* delta, const int32_t* perm, const int32_t* seg_key,
+                        const int32_t* seg_off, const int32_t* n_seg, int64_t n, int K, int n_rate, float* d_rate,
+                        float* d_w, float* scratch, void* stream) {
+    DMT_REQUIRE(n > 0 && K >= 1 && K <= kRowsKMax && n_rate > 0, "dmt_assist_rows_bwd: need n>0 and 1 <= K <= 64");
+    if (d_rate != nullptr) {
+        DMT_CUDA(cudaMemsetAsync(d_rate, 0, sizeof(float) * (size_t)n_rate, as_stream(stream)));
+        int64_t segs = n < n_rate ? n : n_rate;
+        int nbr = (int)((segs + 7) / 8);
+        if (nbr > kAssistBlocks) nbr = kAssistBlocks;
+        assist_rows_rate_grad_kernel<<<nbr, 256, 0, as_stream(stream)>>>(perm, seg_key, seg_off, n_seg, delta, q, d_rate);
+        DMT_LAUNCH_CHECK();
+    }
+    if (d_w != nullptr) {
+        int nb = stream_grid(n, 4);
+        if (nb > kAssistBlocks) nb = kAssistBlocks;
+        assist_rows_w_grad_kernel<<<nb, 256, 0, as_stream(stream)>>>(out, stride_e, stride_j, idx, rate, delta, n, K,
+                                                                     scratch);
+        DMT_LAUNCH_CHECK();
+        assist_rows_w_finish_kernel<<<1, 128, 0, as_stream(stream)>>>(scratch, w, K, nb, d_w);
+        DMT_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -30,6 +30,41 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def assign_orgs(costs, world):
+    """Balanced organization -> rank map (every rank computes the same one from the same inputs): longest-processing-
+    time-first on ``costs`` with the rank's organization COUNT as the first criterion, so no rank stays empty while
+    another holds two (contiguous blocks of ceil(K/world) left ranks idle: 18 organizations on 8 ranks -> 3,3,3,3,3,3,0,0).
+    Returns (orgs_of_rank: list of ascending lists, chunk = max organizations per rank, org_row: row of the
+    rank-blocked matrix O_full [world*chunk x nnz] that holds each organization, rank r's rows being
+    [r*chunk, (r+1)*chunk) — the layout one in-place all-gather fills)."""
+    K = len(costs)
+    order = sorted(range(K), key=lambda k: (-float(costs[k]), k))
+    load = [0.0] * world
+    count = [0] * world
+    mine = [[] for _ in range(world)]
+    for k in order:
+        r = min(range(world), key=lambda q: (count[q], load[q], q))
+        mine[r].append(k)
+        load[r] += float(costs[k])
+        count[r] += 1
+    mine = [sorted(m) for m in mine]
+    chunk = max(1, max(len(m) for m in mine))
+    org_row = [0] * K
+    for r, m in enumerate(mine):
+        for j, k in enumerate(m):
+            org_row[k] = r * chunk + j
+    return mine, chunk, org_row
+
+
+def shard_context():
+    """(rank, world) of the organization sharding behind the drop-in API: active when torch.distributed is initialised
+    with more than one rank (the reference's driver launched under torchrun, one process per GPU), else (0, 1)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+            and os.environ.get("DMT_SHARD", "1") != "0":
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def org_block(K, world, rank):
     """Organizations owned by ``rank``: a contiguous block of ceil(K/world) ids (possibly empty at the tail)."""
     c = -(-K // world)
@@ -53,6 +88,14 @@ def max_over_ranks(value, device):
         return value
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device):
+    if not (dist.is_available() and dist.is_initialized()):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
 
 

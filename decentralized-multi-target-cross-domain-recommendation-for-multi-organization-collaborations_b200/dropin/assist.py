@@ -39,7 +39,29 @@ class Assist:
                 for _ in range(self.num_organizations)]
 
     def make_organization(self):
-        return [Organization(i, self.data_split[i], self.model_name[i]) for i in range(self.num_organizations)]
+        orgs = [Organization(i, self.data_split[i], self.model_name[i]) for i in range(self.num_organizations)]
+        sh = self._sharding()
+        if sh is not None:
+            for r, mine in enumerate(sh['mine']):
+                for i in mine:
+                    orgs[i]._owner_rank = r
+                    orgs[i]._orgs_on_rank = len(mine)
+        return orgs
+
+    def _sharding(self):
+        """Organization -> rank map when the driver runs one process per GPU (torch.distributed initialised, e.g. the
+        unmodified train_recsys_assist.py under torchrun): the reference's loops over organizations
+        (src/train_recsys_assist.py:148-149,169-171) then do real work only for this rank's organizations and
+        Assist.update all-gathers the prediction vectors over NCCL (dist.py). None in a single-process run."""
+        from dmtcdr_b200 import dist as D
+        rank, world = D.shard_context()
+        if world == 1:
+            return None
+        sh = self.__dict__.get('_shard')
+        if sh is None or sh['world'] != world:
+            mine, chunk, org_row = D.assign_orgs([len(s) for s in self.data_split], world)
+            sh = self._shard = {'rank': rank, 'world': world, 'mine': mine, 'chunk': chunk, 'org_row': org_row}
+        return sh
 
     # ------------------------------------------------------------------ device state
     def _mtal(self):
@@ -49,7 +71,10 @@ class Assist:
             for m in y.values():
                 m.sort_indices()
             split = [np.asarray(s.cpu() if isinstance(s, torch.Tensor) else s, dtype=np.int64) for s in self.data_split]
-            self._state = E.MtalState(y, split, cfg['target_mode'], _device())
+            sh = self._sharding()
+            self._state = E.MtalState(y, split, cfg['target_mode'], _device(),
+                                      o_rows=sh['chunk'] * sh['world'] if sh else None,
+                                      org_row=sh['org_row'] if sh else None)
             self._F_dev = {}
         return self._state
 
@@ -108,26 +133,39 @@ class Assist:
     def update(self, organization_outputs, iter):
         """F_t = F_{t-1} + eta[idx] * sum_j softmax(w)_j out_j for every owner, with the optional L-BFGS fit of eta / w
         on the train split and partial alignment (src/assist.py:81-179)."""
-        if 'cs' in cfg and float(cfg['cs']) < 1:
-            raise NotImplementedError("cold-start ('cs' < 1) runs are out of scope (DESIGN.md)")
+        # cold start (12-field control names): organization 0 predicted only the aligned rows it holds; the rest of its
+        # vector is NaN, which selects the softmax(w[1:]) branch of the combine (src/assist.py:109-117,150-157)
+        cold = 'cs' in cfg and float(cfg['cs']) < 1
         st = self._mtal()
         import organization as _org_mod
         for k in organization_outputs[0]:
             for j, out in enumerate(organization_outputs):
                 m = out[k]
-                if m.nnz != st.y[k].nnz:
-                    raise ValueError('organization output {} does not match the target sparsity'.format(j))
+                if getattr(m, '_dmt_remote', False):
+                    continue  # another rank's organization: its row arrives by the all-gather below
                 dev_vals = getattr(m, '_dmt_pred_dev', None)
                 if dev_vals is None:
-                    dev_vals = E.to_dev(np.asarray(m.data, dtype=np.float32), st.device)
-                st.O[k][j].copy_(dev_vals)
+                    vals = np.asarray(m.data, dtype=np.float32)
+                    if m.nnz != st.y[k].nnz:
+                        if not (cold and j == 0 and m.nnz < st.y[k].nnz
+                                and np.array_equal(m.indices, st.y[k].indices_host[:m.nnz])):
+                            raise ValueError('organization output {} does not match the target sparsity'.format(j))
+                        vals = np.concatenate([vals, np.full(st.y[k].nnz - m.nnz, np.nan, np.float32)])
+                    dev_vals = E.to_dev(vals, st.device)
+                elif dev_vals.numel() != st.y[k].nnz:
+                    raise ValueError('organization output {} does not match the target sparsity'.format(j))
+                st.o_row(k, j).copy_(dev_vals)
+        sh = self._sharding()
+        if sh is not None:
+            from dmtcdr_b200 import dist as D
+            D.exchange_outputs(st.O_full, sh['chunk'], sh['rank'], sh['world'])
         # the round's barrier: everything the organizations deferred (train-loss log lines) is written now, before
         # the driver evaluates and resets its logger
         _org_mod.flush_pending()
         a = cfg['assist']
         match_rate = a['match_rate'] if 'match_rate' in a else 1.0
         F_prev = {k: self._F(iter - 1, k) for k in organization_outputs[0]}
-        F_next, fitted = st.update(F_prev, a['ar'], a['ar_mode'], a['aw_mode'], match_rate)
+        F_next, fitted = st.update(F_prev, a['ar'], a['ar_mode'], a['aw_mode'], match_rate, cold=cold)
         for i, (rate, weight) in enumerate(fitted):
             self.ar_state_dict[iter][i] = {'assist_rate': rate.cpu(), 'assist_weight': weight.cpu()}
         if cfg['data_mode'] == 'user':

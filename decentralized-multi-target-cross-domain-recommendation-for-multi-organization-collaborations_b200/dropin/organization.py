@@ -182,6 +182,21 @@ class LazyStateDict(dict):
         return (dict, (dict(self._force()),))
 
 
+_GENS = {}
+
+
+def _seeded_generators(dev, *parts):
+    """Host and device generators seeded per (experiment seed, organization, round): in device-RNG mode an
+    organization's permutations, initial parameters and dropout stream do not depend on which other organizations
+    this process trains, so an organization-sharded run (one process per GPU) reproduces the single-process one."""
+    g = _GENS.get(dev)
+    if g is None:
+        g = _GENS[dev] = (torch.Generator(), torch.Generator(device=dev))
+    g[0].manual_seed(E.he_seed(cfg['seed'], *parts, 1 << 21) & (2 ** 63 - 1))
+    g[1].manual_seed(E.he_seed(cfg['seed'], *parts, 1 << 20) & (2 ** 63 - 1))
+    return g
+
+
 class Organization:
     def __init__(self, organization_id, data_split, model_name):
         self.organization_id = organization_id
@@ -259,6 +274,18 @@ class Organization:
 
     # ------------------------------------------------------------------ local training
     def _engine(self, data_m, target_m):
+        if data_m.shape[0] < target_m.shape[0]:
+            # cold start (src/train_recsys_assist.py:52-56): this organization's train data holds only the first rows
+            # of the aligned entity while targets (and the test split) cover all of them; the engine is sized for the
+            # full row range, rows beyond the data simply carry no data entries
+            pad = self.__dict__.get('_padded')
+            if pad is None or pad[0] is not data_m:
+                ip = np.concatenate([data_m.indptr, np.full(target_m.shape[0] - data_m.shape[0], data_m.indptr[-1],
+                                                            dtype=data_m.indptr.dtype)])
+                pad = (data_m, csr_matrix((data_m.data, data_m.indices, ip),
+                                          shape=(target_m.shape[0], data_m.shape[1])))
+                self._padded = pad
+            data_m = pad[1]
         d = device_csr(data_m)
         t = device_csr(target_m, with_values=False)
         bs = cfg['local']['batch_size']['train']
@@ -280,8 +307,12 @@ class Organization:
             # all organizations of the experiment share this GPU: with many of them the decoder chunk kernel gets the
             # smaller grid that shortens the round (roundloop.DEC_BLOCKS_MANY_ORGS)
             from dmtcdr_b200 import roundloop as _rl
-            n_orgs = int(cfg['num_organizations']) if 'num_organizations' in cfg else 1
+            n_orgs = self.__dict__.get('_orgs_on_rank') or (
+                int(cfg['num_organizations']) if 'num_organizations' in cfg else 1)
             self._eng.h.set_decoder_blocks(_rl.decoder_blocks_for(n_orgs))
+            # few organizations on this GPU: a step's backward pass runs as parallel graph branches (roundloop.py)
+            fan = E.os.environ.get('DMT_FANOUT')
+            self._eng.h.set_fanout((n_orgs <= _rl.FANOUT_MAX_ORGS) if fan is None else fan == '1')
             self._eng_key = key
             self._residual_buf = torch.empty(t.nnz, device=_device())
         return self._eng, d, t
@@ -290,7 +321,13 @@ class Organization:
         """20 local Adam epochs of the AAE on the broadcast residuals (src/organization.py:140-178)."""
         if self.model_name[iter] != 'ae':
             raise TypeError("Organization.train only works with model 'ae' (as in the reference, SURVEY.md top item 1)")
+        if not self._mine():
+            # organization-sharded run (driver launched under torchrun): another rank trains this organization and
+            # its predictions arrive through the all-gather inside Assist.update
+            self.model_state_dict[iter] = None
+            return
         eng, d, t = self._engine(dataset.data, dataset.target)
+        n_own = dataset.data.shape[0]  # the loader walks len(dataset) rows (< the engine's row range under cold start)
         rng = _rng_mode()
         dev = _device()
         if rng == 'reference':
@@ -304,7 +341,8 @@ class Organization:
             # same initial distribution (xavier-uniform weights, zero biases, src/models/ae.py:22-28,89-96) drawn by the
             # device generator straight into the engine's layout: no host init, no upload
             from dmtcdr_b200 import roundloop
-            flat0 = roundloop.init_flat_params(eng.n_enc, eng.n_dec, eng.H1, eng.H2, dev)
+            host_gen, dev_gen = _seeded_generators(dev, self.organization_id, iter)
+            flat0 = roundloop.init_flat_params(eng.n_enc, eng.n_dec, eng.H1, eng.H2, dev, dev_gen)
         res = getattr(dataset.target, '_dmt_residual_dev', None)
         if res is None:
             res = E.to_dev(np.asarray(dataset.target.data, dtype=np.float32), dev)
@@ -318,7 +356,7 @@ class Organization:
         if rng == 'reference':
             losses = []
             for _ in range(n_epochs):
-                lay = E.EpochLayout(E.index_batches(d.shape[0], bs, True), eng.d_len, eng.t_len)
+                lay = E.EpochLayout(E.index_batches(n_own, bs, True), eng.d_len, eng.t_len)
                 keep = [torch.empty(r, eng.H2).bernoulli_(0.5) if a else torch.zeros(r, eng.H2)
                         for r, a in zip(lay.batch_rows, lay.active)]
                 keep = E.to_dev(torch.cat(keep).to(torch.uint8), dev) if keep else None
@@ -328,14 +366,15 @@ class Organization:
                 losses.append(lo)
             loss_all = torch.cat(losses)
         elif eng.plan_epochs >= n_epochs > 1:
-            perms = np.concatenate([torch.randperm(d.shape[0]).numpy() for _ in range(n_epochs)])
-            lay = E.FastEpochLayout(perms, bs, eng.d_len, eng.t_len, epoch_len=d.shape[0])
+            perms = np.concatenate([torch.randperm(n_own, generator=host_gen).numpy() for _ in range(n_epochs)])
+            lay = E.FastEpochLayout(perms, bs, eng.d_len, eng.t_len, epoch_len=n_own)
             layouts.append(lay)
             loss_all = torch.zeros(len(lay.active), device=dev)
             eng.enqueue_round(lay, E.he_seed(cfg['seed'], self.organization_id, iter, 0), hp=hp, loss_out=loss_all)
         else:
             for _ in range(n_epochs):
-                layouts.append(E.FastEpochLayout(torch.randperm(d.shape[0]).numpy(), bs, eng.d_len, eng.t_len))
+                layouts.append(E.FastEpochLayout(torch.randperm(n_own, generator=host_gen).numpy(), bs, eng.d_len,
+                                                 eng.t_len))
             loss_all = torch.zeros(sum(len(l.active) for l in layouts), device=dev)
             seeds = [E.he_seed(cfg['seed'], self.organization_id, iter, e) for e in range(n_epochs)]
             eng.enqueue_epochs(layouts, seeds, hp=hp, loss_out=loss_all)
@@ -359,9 +398,40 @@ class Organization:
             _PENDING.append(sd._log)  # train-loss log lines: written at the round's barrier (Assist.update)
         return
 
+    def _mine(self):
+        """False when another rank of an organization-sharded run owns this organization (set by
+        Assist.make_organization from dist.assign_orgs)."""
+        from dmtcdr_b200 import dist as D
+        owner = self.__dict__.get('_owner_rank')
+        if owner is None:
+            return True
+        rank, world = D.shard_context()
+        return world == 1 or owner == rank
+
+    def _remote_output(self, dataset):
+        """Placeholder for an organization another rank predicts: the target's sparsity with zero values, flagged so
+        that Assist.update takes this organization's vector from the exchange instead."""
+        tm = dataset.target
+        m = csr_matrix((np.zeros(tm.nnz, np.float32), tm.indices, tm.indptr), shape=_shape_target(), copy=False)
+        m._dmt_remote = True
+        return m
+
+    def _short_output(self, out, t, n_pred):
+        """Cold-start output: a CSR with the entries of the rows this organization holds (what the reference's predict
+        assembles from its loader, src/organization.py:186-216); the device copy keeps the global length, NaN beyond."""
+        self._eng.h.signal_current()
+        cut = int(t.indptr_host[n_pred])
+        ip = t.indptr_host.astype(np.int32).copy()
+        ip[n_pred:] = cut
+        m = csr_matrix((E.to_host(out[:cut]).numpy(), t.indices_host[:cut].astype(np.int32), ip), shape=_shape_target())
+        m._dmt_pred_dev = out
+        return m
+
     # ------------------------------------------------------------------ prediction
     def predict(self, dataset, iter):
         """Eval forward at every target position -> CSR with the sparsity of dataset.target (src/organization.py:180-217)."""
+        if not self._mine():
+            return self._remote_output(dataset)
         eng_data = device_csr(dataset.data)
         t = device_csr(dataset.target, with_values=False)
         if getattr(self, '_eng', None) is None:
@@ -379,8 +449,12 @@ class Organization:
             eng.h.wait_current()
             eng.h.set_params(flat)
             self._eng_params_iter = iter
-        out = torch.empty(t.nnz, device=dev)
+        n_pred = min(eng_data.shape[0], t.shape[0])
+        short = n_pred < t.shape[0]  # cold start: rows this organization never saw stay NaN (absent in the reference)
+        out = torch.full((t.nnz,), float('nan'), device=dev) if short else torch.empty(t.nnz, device=dev)
         eng.predict(eng_data, t, out)
+        if short:
+            return self._short_output(out, t, n_pred)
         if 'dmt_sync' in cfg and cfg['dmt_sync']:
             eng.h.signal_current()
             pred = E.to_host(out).numpy()

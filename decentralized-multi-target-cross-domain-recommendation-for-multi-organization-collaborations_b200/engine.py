@@ -280,13 +280,16 @@ class OrgEngine:
         return self.h.get_params()
 
     def predict(self, data: DeviceCSR, target: DeviceCSR, out):
+        """Eval forward at the target positions of the rows the data matrix holds (a cold-start organization's train
+        data is shorter than the global target: positions of the rows beyond it are left untouched)."""
         self.h.wait_current()
+        n_rows = min(data.shape[0], target.shape[0])
         if self.decoder == "tc" and not target.sorted:  # this split's CSR cannot take the windowed epilogue
             self.h.set_decoder_mode("gather")
-            self.h.predict(data.triple(), target.pair(), target.shape[0], out)
+            self.h.predict(data.triple(), target.pair(), n_rows, out)
             self.h.set_decoder_mode("tc")
         else:
-            self.h.predict(data.triple(), target.pair(), target.shape[0], out)
+            self.h.predict(data.triple(), target.pair(), n_rows, out)
         return out
 
     def sync(self):
@@ -300,7 +303,9 @@ class OrgEngine:
 class MtalState:
     """Global per-split state of the coordinator (Assist, reference src/assist.py:13-41) on the device."""
 
-    def __init__(self, y: dict, data_split, target_mode, device="cuda", o_rows=None):
+    def __init__(self, y: dict, data_split, target_mode, device="cuda", o_rows=None, org_row=None):
+        """org_row: row of ``O_full`` that holds each organization's prediction vector (default: row = organization
+        id); the sharded exchange uses a rank-blocked layout so that one in-place all-gather fills it (dist.py)."""
         self.splits = list(y)
         self.y = {k: DeviceCSR(y[k], device) for k in y}
         self.K = len(data_split)
@@ -323,33 +328,57 @@ class MtalState:
         self.data_split = [np.asarray(c, dtype=np.int64) for c in data_split]
         # O may carry padding rows so that an in-place all-gather over equal per-rank chunks can fill it (dist.py)
         self.O_full = {k: torch.zeros(max(self.K, o_rows or 0), self.y[k].nnz, device=device) for k in y}
-        self.O = {k: self.O_full[k][:self.K] for k in y}
+        self.org_row_host = np.arange(self.K, dtype=np.int32) if org_row is None else np.asarray(org_row, np.int32)
+        if len(self.org_row_host) != self.K or len(set(self.org_row_host.tolist())) != self.K:
+            raise ValueError("org_row must give every organization its own row of O")
+        self.org_row = None if org_row is None else torch.from_numpy(self.org_row_host).to(device)
+        self._s_cold_cache = None
+        self.O = {k: self.O_full[k][:self.K] for k in y} if org_row is None else None  # identity layout only
         self._views = {}
         self._eval_meta = {}
         self._combine_cache = None
 
+    def O_orgmajor(self, split):
+        """[K x nnz] copy in organization order (tests / inspection; the kernels index O_full through org_row)."""
+        return self.O_full[split][torch.from_numpy(self.org_row_host.astype(np.int64)).to(self.device)]
+
+    def o_row(self, split, org):
+        """Organization ``org``'s prediction vector for ``split`` (a row view of O_full)."""
+        return self.O_full[split][int(self.org_row_host[org])]
+
     def residual(self, F, split, clamp, out=None):
         return native.residual(F, self.y[split].data, self.loss_kind, 1.0 if clamp else 0.0, out)
 
-    def evaluate(self, F, split="test", block_rows=500, topk=10):
+    def evaluate(self, F, split="test", block_rows=500, topk=10, org=None):
         """Global metrics of the current prediction with the reference's test loop semantics
         (src/train_recsys_assist.py:175-217, src/logger.py:35-55) computed on the device: per-block Loss and
-        RMSE (explicit) or NDCG@topk (implicit), entry-weighted over blocks. One launch + a [n_blocks x 3] read-back."""
+        RMSE (explicit) or NDCG@topk (implicit), entry-weighted over blocks. One launch + a [n_blocks x 3] read-back.
+        org: score only that organization's columns (cold-start runs are scored on organization 0's,
+        src/train_recsys_assist.py:180-182)."""
         y = self.y[split]
         n_rows = y.shape[0]
-        key = (split, block_rows, topk)
+        key = (split, block_rows, topk, org)
         if key not in self._eval_meta:
-            ip = y.indptr_host
+            ip, ix = y.indptr_host, y.indices_host
+            pos_dev = None
+            if org is not None:
+                pos = self.owner_view(split, org)["pos_host"]
+                cnt = np.bincount(np.searchsorted(ip, pos, side="right") - 1, minlength=n_rows)[:n_rows]
+                ip = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+                ix = ix[pos]
+                pos_dev = torch.from_numpy(pos.astype(np.int64)).to(self.device)
             edges = np.arange(0, n_rows + block_rows, block_rows).clip(max=n_rows)
             m = (ip[edges[1:]] - ip[edges[:-1]]).astype(np.float64)          # entries per block
             rl = np.diff(ip) > 0
             rows_nz = np.add.reduceat(rl, edges[:-1]).astype(np.float64) if n_rows else np.zeros(0)
-            k = np.array([min(topk, len(np.unique(y.indices_host[ip[a]:ip[b]]))) for a, b in zip(edges[:-1], edges[1:])],
+            k = np.array([min(topk, len(np.unique(ix[ip[a]:ip[b]]))) for a, b in zip(edges[:-1], edges[1:])],
                          dtype=np.int32)
-            self._eval_meta[key] = (m, rows_nz, to_dev(k, self.device))
-        m, rows_nz, k_dev = self._eval_meta[key]
+            ip_dev = y.indptr if org is None else to_dev(ip.astype(np.int32), self.device)
+            self._eval_meta[key] = (m, rows_nz, to_dev(k, self.device), ip_dev, pos_dev)
+        m, rows_nz, k_dev, ip_dev, pos_dev = self._eval_meta[key]
         implicit = self.target_mode == "implicit"
-        sums = to_host(native.eval_blocks(y.indptr, F, y.data, n_rows, block_rows, self.loss_kind,
+        pred, tgt = (F, y.data) if pos_dev is None else (F[pos_dev].contiguous(), y.data[pos_dev].contiguous())
+        sums = to_host(native.eval_blocks(ip_dev, pred, tgt, n_rows, block_rows, self.loss_kind,
                                           k_dev if implicit else None)).double().numpy()
         ok = m > 0
         w = m[ok] / m[ok].sum()
@@ -396,10 +425,11 @@ class MtalState:
             ends.append(pos[n_match] if n_match < len(pos) else self.y[split].nnz)
         return torch.tensor(ends, dtype=torch.int64, device=self.device)
 
-    def fit_owner(self, i, F_prev, ar, ar_mode, aw_mode, match_rate, lr=0.1, steps=10):
+    def fit_owner(self, i, F_prev, ar, ar_mode, aw_mode, match_rate, lr=0.1, steps=10, cold=False):
         """L-BFGS fit of owner i's assisted learning rates / assistance weights on the train split
         (src/assist.py:118-129). The two-loop recursion runs on tiny host vectors (torch.optim.LBFGS, as in the
-        reference); every closure evaluation is ONE fused loss+gradient kernel over the owner's [n_i x K] view."""
+        reference); every closure evaluation is ONE fused loss+gradient kernel over the owner's [n_i x K] view
+        (cold start: the NaN-aware forward / backward pair of the differentiable module, dmt_assist_rows_*)."""
         n_rate = self.split_sizes[i]
         rate = torch.full((n_rate,), float(ar))
         weight = torch.ones(self.K) / self.K
@@ -413,15 +443,33 @@ class MtalState:
         if not free:
             return rate, weight
         v = self.owner_view("train", i)
-        n_match = int(v["n"] * match_rate) if match_rate < 1 else v["n"]
-        h, t, V = native.assist_gather_view(F_prev, self.y["train"].data, self.O["train"], v["pos"], v["rank"], i,
-                                            n_match)
+        n = v["n"]
+        n_match = int(n * match_rate) if match_rate < 1 else n
+        h, t, V = native.assist_gather_view(F_prev, self.y["train"].data, self.O_full["train"], v["pos"], v["rank"], i,
+                                            n_match, org_row=self.org_row, K=self.K)
         scratch = torch.empty(native.load().dmt_assist_scratch_floats(self.K), device=self.device)
         opt = torch.optim.LBFGS(free, lr=lr)
+        # all closure inputs / outputs of one evaluation travel in ONE pinned staging pair (no pageable copies, one sync)
+        stage_in = torch.empty(n_rate + self.K, dtype=torch.float32, pin_memory=True)
+        dev_in = torch.empty(n_rate + self.K, device=self.device)
+        if cold:
+            if "idx" not in v:
+                seg = v["seg_off"].cpu().numpy()
+                v["idx"] = torch.from_numpy(np.repeat(np.arange(n_rate, dtype=np.int32), np.diff(seg))).to(self.device)
+                v["seg"] = native.sort_segments(v["idx"], n_rate)
 
         def closure():
-            out = to_host(native.assist_loss_grad(h, t, V, v["seg_off"], to_dev(rate.detach(), self.device),
-                                                  to_dev(weight.detach(), self.device), self.loss_kind, scratch))
+            stage_in[:n_rate].copy_(rate.detach())
+            stage_in[n_rate:].copy_(weight.detach())
+            dev_in.copy_(stage_in, non_blocking=True)
+            r_d, w_d = dev_in[:n_rate], dev_in[n_rate:]
+            if cold:
+                tgt, q = native.assist_rows_fwd(V, 1, n, h, v["idx"], r_d, w_d, n, self.K)
+                dpred, sums = native.loss_fwd(tgt, t, self.loss_kind, True)
+                d_rate, d_w = native.assist_rows_bwd(V, 1, n, v["idx"], r_d, w_d, q, dpred, v["seg"], n, self.K)
+                out = to_host(torch.cat([sums[:1], d_rate, d_w])) / n
+            else:
+                out = to_host(native.assist_loss_grad(h, t, V, v["seg_off"], r_d, w_d, self.loss_kind, scratch))
             if rate.requires_grad:
                 rate.grad = out[1:1 + n_rate].clone()
             if weight.requires_grad:
@@ -432,25 +480,33 @@ class MtalState:
             opt.step(closure)
         return rate.detach(), weight.detach()
 
-    def update(self, F_prev: dict, ar, ar_mode="constant", aw_mode="constant", match_rate=1.0, out=None):
-        """Assist.update (src/assist.py:81-179): fit per owner on train, then ONE combine pass per split."""
-        fitted = [self.fit_owner(i, F_prev["train"], ar, ar_mode, aw_mode, match_rate) for i in range(self.K)]
+    def update(self, F_prev: dict, ar, ar_mode="constant", aw_mode="constant", match_rate=1.0, out=None, cold=False):
+        """Assist.update (src/assist.py:81-179): fit per owner on train, then ONE combine pass per split.
+        cold: cold-start run — organization 0's output is NaN on the aligned rows it never saw; those entries combine
+        organizations 1.. with softmax(w[1:]) (src/models/assist.py:28-34)."""
+        fitted = [self.fit_owner(i, F_prev["train"], ar, ar_mode, aw_mode, match_rate, cold=cold)
+                  for i in range(self.K)]
         rate_col = np.zeros(self.n_cols, np.float32)
         S = np.zeros((self.K, self.K), np.float32)
+        S_cold = np.zeros((self.K, self.K), np.float32) if cold else None
         for i, (rate, weight) in enumerate(fitted):
             rate_col[self.data_split[i]] = rate.numpy()
             S[i] = torch.softmax(weight, -1).numpy()
+            if cold and self.K > 1:
+                S_cold[i, 1:] = torch.softmax(weight[1:], -1).numpy()
         # constant rates / weights repeat every round: upload once (a pageable copy on the compute stream would make the
         # host wait for the whole round that the stream is still ordered behind)
-        ck = (rate_col.tobytes(), S.tobytes())
+        ck = (rate_col.tobytes(), S.tobytes(), cold)
         if self._combine_cache is None or self._combine_cache[0] != ck:
-            self._combine_cache = (ck, to_dev(rate_col, self.device), to_dev(S, self.device))
-        rate_col_d, S_d = self._combine_cache[1], self._combine_cache[2]
+            self._combine_cache = (ck, to_dev(rate_col, self.device), to_dev(S, self.device),
+                                   to_dev(S_cold, self.device) if cold else None)
+        rate_col_d, S_d, S_cold_d = self._combine_cache[1], self._combine_cache[2], self._combine_cache[3]
         F_next = {}
         for k in self.splits:
             me = self.match_end(k, match_rate) if match_rate < 1 else None
-            F_next[k] = native.assist_combine(F_prev[k], self.O[k], self.y[k].indices, self.owner, rate_col_d, S_d, me,
-                                              out[k] if out is not None else None)
+            F_next[k] = native.assist_combine(F_prev[k], self.O_full[k], self.y[k].indices, self.owner, rate_col_d, S_d,
+                                              me, out[k] if out is not None else None, org_row=self.org_row,
+                                              S_cold=S_cold_d, K=self.K)
         return F_next, fitted
 
 

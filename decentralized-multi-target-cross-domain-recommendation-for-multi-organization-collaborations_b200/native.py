@@ -50,8 +50,11 @@ def _declare(lib):
         "dmt_version": (I, []),
         "dmt_check_device": (I, []),
         "dmt_residual": (I, [P, P, P, L, I, F, P]),
-        "dmt_assist_combine": (I, [P, P, P, P, P, P, P, P, L, I, P]),
-        "dmt_assist_gather_view": (I, [P, P, P, P, P, L, L, I, I, L, P, P, P, P]),
+        "dmt_assist_combine": (I, [P, P, P, P, P, P, P, P, L, I, P, P, P]),
+        "dmt_assist_gather_view": (I, [P, P, P, P, P, L, L, I, I, L, P, P, P, P, P]),
+        "dmt_assist_rows_fwd": (I, [P, L, L, P, P, P, P, L, I, P, P, P]),
+        "dmt_assist_rows_scratch_floats": (L, [I]),
+        "dmt_assist_rows_bwd": (I, [P, L, L, P, P, P, P, P, P, P, P, P, L, I, I, P, P, P, P]),
         "dmt_assist_scratch_floats": (L, [I]),
         "dmt_assist_loss_grad": (I, [P, P, P, P, P, P, L, I, I, I, P, P, P, P, P]),
         "dmt_base_fit": (I, [P, P, L, P, P, P]),
@@ -162,25 +165,53 @@ def residual(F, y, loss_kind, clamp=0.0, out=None):
     return out
 
 
-def assist_combine(F_old, O, col, owner, rate_col, S, match_end=None, out=None):
+def assist_combine(F_old, O, col, owner, rate_col, S, match_end=None, out=None, org_row=None, S_cold=None, K=None):
+    """O: [rows x nnz]; K organizations (default: rows) whose rows are org_row[j] (default j)."""
     lib = load()
-    K, nnz = O.shape
+    rows, nnz = O.shape
+    K = rows if K is None else K
     out = torch.empty_like(F_old) if out is None else out
     check(lib.dmt_assist_combine(ptr(F_old), ptr(O), ptr(col), ptr(owner), ptr(rate_col), ptr(S), ptr(match_end),
-                                 ptr(out), nnz, K, stream()), "dmt_assist_combine")
+                                 ptr(out), nnz, K, ptr(org_row), ptr(S_cold), stream()), "dmt_assist_combine")
     return out
 
 
-def assist_gather_view(F_old, y, O, pos, rank, owner, n_match):
+def assist_gather_view(F_old, y, O, pos, rank, owner, n_match, org_row=None, K=None):
     lib = load()
-    K, nnz = O.shape
+    rows, nnz = O.shape
+    K = rows if K is None else K
     n = pos.numel()
     h = torch.empty(n, device=O.device, dtype=torch.float32)
     t = torch.empty_like(h)
     V = torch.empty(K, n, device=O.device, dtype=torch.float32)
     check(lib.dmt_assist_gather_view(ptr(F_old), ptr(y), ptr(O), ptr(pos), ptr(rank), nnz, n, K, owner, n_match,
-                                     ptr(h), ptr(t), ptr(V), stream()), "dmt_assist_gather_view")
+                                     ptr(h), ptr(t), ptr(V), ptr(org_row), stream()), "dmt_assist_gather_view")
     return h, t, V
+
+
+def assist_rows_fwd(out, stride_e, stride_j, history, idx, rate, w, n, K, want_q=True):
+    """models.Assist forward over n entries (cold-start aware) -> target, q."""
+    lib = load()
+    tgt = torch.empty(n, device=history.device, dtype=torch.float32)
+    q = torch.empty(n, device=history.device, dtype=torch.float32) if want_q else None
+    check(lib.dmt_assist_rows_fwd(ptr(out), stride_e, stride_j, ptr(history), ptr(idx), ptr(rate), ptr(w), n, K,
+                                  ptr(tgt), ptr(q), stream()), "dmt_assist_rows_fwd")
+    return tgt, q
+
+
+def assist_rows_bwd(out, stride_e, stride_j, idx, rate, w, q, delta, seg, n, K, want_rate=True, want_w=True):
+    """-> d_rate [n_rate] or None, d_w [K] or None. seg = sort_segments(idx, n_rate)."""
+    lib = load()
+    n_rate = rate.numel()
+    dev = rate.device
+    d_rate = torch.empty(n_rate, device=dev, dtype=torch.float32) if want_rate else None
+    d_w = torch.empty(K, device=dev, dtype=torch.float32) if want_w else None
+    scratch = torch.empty(lib.dmt_assist_rows_scratch_floats(K), device=dev, dtype=torch.float32)
+    perm, seg_key, seg_off, n_seg = seg
+    check(lib.dmt_assist_rows_bwd(ptr(out), stride_e, stride_j, ptr(idx), ptr(rate), ptr(w), ptr(q), ptr(delta),
+                                  ptr(perm), ptr(seg_key), ptr(seg_off), ptr(n_seg), n, K, n_rate, ptr(d_rate),
+                                  ptr(d_w), ptr(scratch), stream()), "dmt_assist_rows_bwd")
+    return d_rate, d_w
 
 
 def assist_loss_grad(h, t, V, seg_off, rate, w, loss_kind, scratch=None):

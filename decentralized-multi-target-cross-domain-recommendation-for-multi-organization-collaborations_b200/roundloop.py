@@ -81,10 +81,17 @@ class AssistRounds:
         y = {k: mats[k][1] for k in mats}
         for m in y.values():
             m.sort_indices()
-        self.chunk = -(-self.K // world)  # organizations per rank (contiguous blocks -> in-place all-gather)
-        self.state = E.MtalState(y, cols, target_mode, device, o_rows=self.chunk * world)
+        # organizations -> ranks, balanced by count then by work (target entries are the same for every organization;
+        # the data entries and the encoder's share of the parameters differ); rank r's rows of O_full are
+        # [r*chunk, (r+1)*chunk) so ONE in-place all-gather per split publishes them (dist.py)
+        from . import dist as D
+        d_nnz = np.diff(mats["train"][0].tocsc().indptr)
+        costs = [float(y["train"].nnz + 2 * d_nnz[c].sum()) for c in cols]
+        owned, self.chunk, org_row = D.assign_orgs(costs, world)
+        self.state = E.MtalState(y, cols, target_mode, device, o_rows=self.chunk * world,
+                                 org_row=org_row if world > 1 else None)
         self.n_rows = y["train"].shape[0]
-        self.my_orgs = list(range(rank * self.chunk, min(self.K, (rank + 1) * self.chunk)))
+        self.my_orgs = owned[rank]
         self.org_data, self.org_test_data, self.eng = {}, {}, {}
         # One plan + one graph per organization and ROUND (instead of per local epoch) when the plan buffers fit: ~40 B
         # per target entry and planned epoch, i.e. 0.7 GB per organization at ML1M shape with 20 epochs. Same batches,
@@ -282,8 +289,8 @@ class AssistRounds:
         st = self.state
         for org in self.my_orgs:
             eng = self.eng[org]
-            eng.predict(self.org_data[org], st.y["train"], st.O["train"][org])
-            eng.predict(self.org_test_data[org], st.y["test"], st.O["test"][org])
+            eng.predict(self.org_data[org], st.y["train"], st.o_row("train", org))
+            eng.predict(self.org_test_data[org], st.y["test"], st.o_row("test", org))
         for org in self.my_orgs:
             self.eng[org].h.signal_current()  # the current stream waits for every organization's stream
         self.round_losses[t] = loss_bufs

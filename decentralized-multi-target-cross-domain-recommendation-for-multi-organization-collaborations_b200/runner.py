@@ -143,6 +143,9 @@ def evaluate(assist, metric, logger, epoch):
 
     F = assist.organization_output[epoch]['test']
     y = assist.organization_target[0]['test']
+    if 'cs' in cfg:  # cold-start runs are scored on organization 0's columns (src/train_recsys_assist.py:180-182)
+        cols0 = np.asarray(assist.data_split[0])
+        F, y = F[:, cols0], y[:, cols0]
     bs = cfg[cfg['model_name']]['batch_size']['test']
     mode = cfg['data_mode']
     for s in range(0, F.shape[0], bs):
@@ -176,6 +179,10 @@ def run_assist_experiment(data, control_name, seed=0, local_epochs=None, rounds=
     process_dataset(dataset)
     data_split = split_dataset(dataset)
     dataset = make_split_dataset(dataset, data_split)
+    if 'cs' in cfg:  # cold start: organization 0 keeps the first int(n*cs) aligned rows (src/train_recsys_assist.py:52-56)
+        start_size = int(len(dataset[0]['train']) * cfg['cs'])
+        dataset[0]['train'].data = dataset[0]['train'].data[:start_size]
+        dataset[0]['train'].target = dataset[0]['train'].target[:start_size]
     assist = assist_mod.Assist(data_split)
     organization = assist.make_organization()
     names = ['Loss', 'RMSE'] if cfg['target_mode'] == 'explicit' else ['Loss', 'NDCG']

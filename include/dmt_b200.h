@@ -48,17 +48,21 @@ int dmt_residual(const float* F, const float* y, float* r, int64_t n, int loss_k
  * src/models/assist.py:36-37):  F_new[p] = F_old[p] + rate_col[col[p]] * sum_j S[owner[col[p]]][j] * O'[j][p]
  * with O'[j][p] = O[j][p] if p < match_end[owner] else O[owner][p]   (partial alignment, src/assist.py:95-103).
  * O is org-major [K][nnz]; S is the row-wise softmax of every owner's assistance weights, [K][K] row-major;
- * rate_col[c] = assist_rate of the owner of column c at c's local index. */
+ * rate_col[c] = assist_rate of the owner of column c at c's local index.
+ * org_row (may be NULL = identity): row of O that holds organization j (rank-blocked layouts of the sharded exchange).
+ * S_cold (may be NULL): cold start (src/assist.py:109-117,150-157; src/models/assist.py:28-34) - wherever organization
+ * 0's output is NaN (aligned rows organization 0 never saw) the sum runs over j >= 1 with S_cold[owner][j] =
+ * softmax(w_owner[1:])[j-1], S_cold[owner][0] = 0. */
 int dmt_assist_combine(const float* F_old, const float* O, const int32_t* col, const int32_t* owner,
                        const float* rate_col, const float* S, const int64_t* match_end, float* F_new,
-                       int64_t nnz, int K, void* stream);
+                       int64_t nnz, int K, const int32_t* org_row, const float* S_cold, void* stream);
 
 /* Gather one owner's view for the L-BFGS fit (src/assist.py:93-117): for e in [0,n): p = pos[e];
  * h[e]=F_old[p], t[e]=y[p], V[j][e] = (rank[e] < n_match ? O[j][p] : O[owner][p]). pos is the owner's entries in
  * column-sorted order, rank[e] the entry's rank in the original (row-major) order. V is [K][n]. */
 int dmt_assist_gather_view(const float* F_old, const float* y, const float* O, const int32_t* pos,
                            const int32_t* rank, int64_t nnz, int64_t n, int K, int owner, int64_t n_match, float* h,
-                           float* t, float* V, void* stream);
+                           float* t, float* V, const int32_t* org_row, void* stream);
 
 /* Fused loss + gradient of models.Assist for one owner (src/models/assist.py:25-40, closure src/assist.py:121-126).
  * Entries are column-sorted; seg_off[n_rate+1] delimits the entries of each owned column (local index = segment).
@@ -68,6 +72,21 @@ int64_t dmt_assist_scratch_floats(int K);
 int dmt_assist_loss_grad(const float* h, const float* t, const float* V, const int32_t* seg_off, const float* rate,
                          const float* w, int64_t n, int n_rate, int K, int loss_kind, float* out_loss, float* d_rate,
                          float* d_w, float* scratch, void* stream);
+
+/* models.Assist as a differentiable module (src/models/assist.py:25-40; the closure at src/assist.py:121-126 calls
+ * loss.backward() through it). out is the [n x K] stack of the organizations' outputs addressed as
+ * out[e*stride_e + j*stride_j]; target[e] = history[e] + rate[idx[e]] * sum_j softmax(w)_j out[e][j]; entries whose slot 0
+ * is NaN (cold start) use sum_{j>=1} softmax(w[1:])_j out[e][j] instead. q[e] (may be NULL) keeps the weighted sum.
+ * bwd: given delta[e] = dLoss/dtarget[e]: d_rate[c] = sum_{e: idx[e]=c} delta[e] q[e] (perm / seg_* = dmt_sort_segments
+ * of idx; columns without entries get 0), d_w = gradient w.r.t. the UN-normalised weights through both softmaxes.
+ * d_rate or d_w may be NULL. scratch >= dmt_assist_rows_scratch_floats(K). Deterministic (no atomics). */
+int dmt_assist_rows_fwd(const float* out, int64_t stride_e, int64_t stride_j, const float* history, const int32_t* idx,
+                        const float* rate, const float* w, int64_t n, int K, float* target, float* q, void* stream);
+int64_t dmt_assist_rows_scratch_floats(int K);
+int dmt_assist_rows_bwd(const float* out, int64_t stride_e, int64_t stride_j, const int32_t* idx, const float* rate,
+                        const float* w, const float* q, const float* delta, const int32_t* perm, const int32_t* seg_key,
+                        const int32_t* seg_off, const int32_t* n_seg, int64_t n, int K, int n_rate, float* d_rate,
+                        float* d_w, float* scratch, void* stream);
 
 /* Round-0 predictor models.Base (src/models/base.py:22-60). fit: base[idx] += rating, count[idx] += 1.
  * predict (explicit): base/(count+1e-10), unseen columns -> mean of the seen means (fill computed here);

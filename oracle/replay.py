@@ -109,6 +109,7 @@ def run_experiment(data, control, seed=0, local_epochs=20, rounds=10, batch_size
     aw_mode = f[8]
     match_rate = float(f[9]) if len(f) > 9 else 1.0
     pl = f[10] if len(f) > 10 else "none"
+    cs = float(f[11]) if len(f) > 11 else None  # cold start: 'cs' in cfg only for 12-field names (src/config.py:12-15)
     K = {"ML100K": 18, "ML1M": 18, "Douban": 3, "Amazon": 4}[data_name] if "genre" in split_mode else int(
         split_mode.split("-")[1])
     bs_table = {"user": {"ML100K": 100, "ML1M": 500, "Douban": 100, "Amazon": 500},
@@ -122,6 +123,21 @@ def run_experiment(data, control, seed=0, local_epochs=20, rounds=10, batch_size
     org_data = [{k: mats[k][0][:, c].tocsr() for k in mats} for c in cols]
     org_tgt0 = [{k: mats[k][1][:, c].tocsr() for k in mats} for c in cols]
     y = {k: mats[k][1] for k in mats}  # canonical global CSR, values = ground truth
+    start = n_rows
+    if cs is not None:
+        # src/train_recsys_assist.py:52-56: organization 0 keeps only the first int(n*cs) aligned rows of its TRAIN
+        # split; the global train target is assembled from the organizations' targets (:98-141), so organization 0's
+        # columns carry no entries below that row
+        start = int(n_rows * cs)
+        org_data[0]["train"] = org_data[0]["train"][:start]
+        org_tgt0[0]["train"] = org_tgt0[0]["train"][:start]
+        coo = y["train"].tocoo()
+        own0 = np.zeros(n_cols, bool)
+        own0[cols[0]] = True
+        keep = ~(own0[coo.col] & (coo.row >= start))
+        from scipy.sparse import csr_matrix
+        y["train"] = csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=y["train"].shape)
+        y["train"].sort_indices()
     indices = {k: y[k].indices for k in y}
     views = {k: mtal.owner_views(indices[k], cols, n_cols) for k in y}
     # ---- round 0: Organization.initialize per organization (src/organization.py:29-138) ----
@@ -135,7 +151,15 @@ def run_experiment(data, control, seed=0, local_epochs=20, rounds=10, batch_size
         for k in y:
             # local CSR order of the organization == global order restricted to its columns
             F[0][k][views[k][i][0]] = _to_global_order(org_tgt0[i][k], preds[k])
-    metrics = {0: ometrics.evaluate(F[0]["test"], y["test"], data_mode, target_mode, bs)}
+    def test_metrics(Ft):
+        if cs is None:
+            return ometrics.evaluate(Ft, y["test"], data_mode, target_mode, bs)
+        # src/train_recsys_assist.py:180-182: cold-start runs are scored on organization 0's columns only
+        sub = _with_data(y["test"], np.arange(y["test"].nnz, dtype=np.float64))[:, cols[0]].tocsr()
+        pos = sub.data.astype(np.int64)
+        return ometrics.evaluate(np.asarray(Ft)[pos], _with_values64(sub, y["test"].data[pos]), data_mode, target_mode, bs)
+
+    metrics = {0: test_metrics(F[0]["test"])}
     fitted = [None]
     org0_sd1 = None
     clamp = mtal.needs_clamp(data_name, data_mode, target_mode)
@@ -157,8 +181,9 @@ def run_experiment(data, control, seed=0, local_epochs=20, rounds=10, batch_size
             p0 = init_ae_params(org_data[i]["train"].shape[1], n_cols)
             epoch_batches, masks = [], []
             # masks must be drawn interleaved with the sampler draws, so walk the epochs now
+            n_i = org_data[i]["train"].shape[0]  # organization 0 under cold start walks its truncated row range
             for _ in range(local_epochs):
-                batches = loader_batches(n_rows, bs, True)
+                batches = loader_batches(n_i, bs, True)
                 epoch_batches.append(batches)
                 for rows in batches:
                     b = train.make_batch(org_data[i]["train"], tgt["train"], rows, data_mode)
@@ -179,17 +204,27 @@ def run_experiment(data, control, seed=0, local_epochs=20, rounds=10, batch_size
                 init_ae_params(org_data[i][k].shape[1], n_cols)  # predict() builds a fresh model before loading
                 loader_batches(1, 1, False)
                 o[k] = train.predict_org_ae(params[i], org_data[i][k], tgt[k], data_mode, target_mode, bs)
+                if org_data[i][k].shape[0] < n_rows:
+                    # rows the organization never saw are absent from its output (src/organization.py:186-216): NaN
+                    # here, which is what the padding at src/assist.py:109-111,150-152 produces for the other owners
+                    o[k][tgt[k].indptr[org_data[i][k].shape[0]]:] = np.nan
             org_out.append(o)
         # ---- update (src/assist.py:81-179) ----
         Fn, fit = mtal.update(F[t - 1], {k: y[k].data for k in y}, org_out, indices, cols, n_cols, target_mode, ar,
                               ar_mode, aw_mode, match_rate)
         F.append(Fn)
         fitted.append(fit)
-        metrics[t] = ometrics.evaluate(Fn["test"], y["test"], data_mode, target_mode, bs)
+        metrics[t] = test_metrics(Fn["test"])
     return {"F": F, "fitted": fitted, "metrics": metrics, "org0_sd1": org0_sd1, "data_split": cols, "y": y}
 
 
 def _with_data(m, values):
+    out = m.copy()
+    out.data = np.asarray(values, dtype=np.float32)
+    return out
+
+
+def _with_values64(m, values):
     out = m.copy()
     out.data = np.asarray(values, dtype=np.float32)
     return out

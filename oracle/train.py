@@ -107,7 +107,7 @@ def train_org_ae(params, data, target, data_mode, target_mode, epoch_batches, ma
 def predict_org_ae(params, data, target, data_mode, target_mode, batch_size):
     """Organization.predict (reference src/organization.py:180-217): sequential batches, eval forward at every
     target position, skip batches without targets; returns values in the target CSR's storage order."""
-    n = target.shape[0]
+    n = min(target.shape[0], data.shape[0])  # a cold-start organization only walks the rows it holds (len = data rows)
     out = np.zeros(target.nnz, dtype=np.float32)
     with torch.no_grad():
         for s in range(0, n, batch_size):

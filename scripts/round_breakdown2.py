@@ -32,8 +32,8 @@ for org in R.my_orgs:
 for org in R.my_orgs:
     eng = R.eng[org]
     t0 = time.perf_counter()
-    eng.predict(R.org_data[org], st.y["train"], st.O["train"][org])
-    eng.predict(R.org_test_data[org], st.y["test"], st.O["test"][org])
+    eng.predict(R.org_data[org], st.y["train"], st.o_row("train", org))
+    eng.predict(R.org_test_data[org], st.y["test"], st.o_row("test", org))
     tick("predict", t0)
 t0 = time.perf_counter()
 for org in R.my_orgs:

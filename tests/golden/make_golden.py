@@ -48,6 +48,14 @@ CASES = {
     "round_amazon_user_implicit": ("round", "Amazon_user_implicit_ae_0_genre_assist_constant-0.1_optim_0.5_dp-10",
                                    "tiny-Amazon"),
     "round_ml_item_explicit": ("round", "ML100K_item_explicit_ae_0_random-4_assist_optim-0.1_constant", "tiny-ML100K"),
+    # cold start (12-field control name, src/train_recsys_assist.py:52-56,180-182; src/assist.py:109-117,150-157;
+    # src/models/assist.py:28-34): organization 0 holds only the first half of the aligned rows
+    "round_ml_user_explicit_cs": ("round", "ML100K_user_explicit_ae_0_genre_assist_constant-0.3_constant_1_none_0.5",
+                                  "tiny-ML100K"),
+    # joint driver (src/train_recsys_joint.py:40-199): joint training epochs, models.distribute, the per-organization
+    # test() loop with its combined metrics
+    "joint_mf_user_explicit": ("joint", "ML100K_user_explicit_mf_0_genre_joint", "tiny-ML100K"),
+    "joint_nmf_user_implicit": ("joint", "ML100K_user_implicit_nmf_0_genre_joint", "tiny-ML100K"),
 }
 
 
@@ -94,6 +102,10 @@ def start_assist(ns, local_epochs, rounds):
     ns.utils.process_dataset(dataset)
     data_split = ns.data.split_dataset(dataset)
     dataset = ns.data.make_split_dataset(data_split)
+    if "cs" in cfg:  # the driver's own cold-start truncation (src/train_recsys_assist.py:52-56)
+        start_size = int(len(dataset[0]["train"]) * cfg["cs"])
+        dataset[0]["train"].data = dataset[0]["train"].data[:start_size]
+        dataset[0]["train"].target = dataset[0]["train"].target[:start_size]
     assist = ns.assist.Assist(data_split)
     organization = assist.make_organization()
     names = ["Loss", "RMSE"] if cfg["target_mode"] == "explicit" else ["Loss", "NDCG"]
@@ -235,8 +247,15 @@ def capture_round_inputs(out, ns, dataset, assist, organization, metric, logger,
     for k in ("train", "test"):
         ref = assist.organization_target[0][k]
         for j, o in enumerate(outs):
-            assert np.array_equal(o[k].indptr, ref.indptr) and np.array_equal(o[k].indices, ref.indices)
-            out["r{}/org_out/{}/{}".format(t, k, j)] = o[k].data.astype(np.float32)
+            vals = o[k].data.astype(np.float32)
+            if o[k].nnz != ref.nnz:
+                # cold start: the organization predicted only the rows it holds; the rest of the global pattern is
+                # absent from its output (the reference pads it with NaN at src/assist.py:109-111)
+                assert np.array_equal(o[k].indices, ref.indices[:o[k].nnz])
+                vals = np.concatenate([vals, np.full(ref.nnz - o[k].nnz, np.nan, np.float32)])
+            else:
+                assert np.array_equal(o[k].indptr, ref.indptr) and np.array_equal(o[k].indices, ref.indices)
+            out["r{}/org_out/{}/{}".format(t, k, j)] = vals
     return dataset, outs
 
 
@@ -321,9 +340,58 @@ def case_round(case, ns):
     return out
 
 
+def case_joint(case, ns):
+    """Two epochs of the joint driver's own loop (src/train_recsys_joint.py:93-97: train, models.distribute, test) on
+    the tiny dataset: the initial joint state_dict, every epoch's sampler order, the state_dict after every epoch and
+    the test metrics the driver logs from the DISTRIBUTED local models (per-organization Loss + combined RMSE/NDCG)."""
+    import copy
+    import torch
+
+    cfg = ns.cfg
+    out = {}
+    name = cfg["model_name"]
+    dataset = ns.data.fetch_dataset(cfg["data_name"], verbose=False)
+    ns.utils.process_dataset(dataset)
+    data_split = ns.data.split_dataset(dataset)
+    for i, s in enumerate(data_split):
+        out["data_split/{}".format(i)] = s.numpy().astype(np.int64)
+    data_loader = ns.data.make_data_loader(dataset, name)
+    model = eval("ns.models.{}()".format(name))
+    put_dict(out, "sd0", model.state_dict())
+    optimizer = ns.utils.make_optimizer(model, name)
+    names = ["Loss", "RMSE"] if cfg["target_mode"] == "explicit" else ["Loss", "NDCG"]
+    metric = ns.metrics.Metric({"train": names, "test": names})
+    logger = ns.logger.make_logger("output/runs/golden")
+    local_dataset = ns.data.make_split_dataset(data_split)
+    local_loader, local_model = [], []
+    for i in range(len(local_dataset)):
+        local_loader.append(ns.data.make_data_loader(local_dataset[i], name)["test"])
+        nu = local_dataset[i]["train"].num_users["data"]
+        ni = local_dataset[i]["train"].num_items["data"]
+        local_model.append(eval("ns.models.{}(nu, ni)".format(name)))
+    metrics = {}
+    for epoch in (1, 2):
+        st = torch.get_rng_state()
+        it = iter(data_loader["train"])
+        order = [np.asarray(b, dtype=np.int64) for b in it._sampler_iter]
+        torch.set_rng_state(st)
+        out["e{}/rows".format(epoch)] = np.concatenate(order)
+        out["e{}/batch_sizes".format(epoch)] = np.array([len(b) for b in order], dtype=np.int64)
+        ns.driver.train(data_loader["train"], model, optimizer, metric, logger, epoch)
+        ns.models.distribute(model, local_model, data_split)
+        ns.driver.test(local_loader, data_split, local_model, metric, logger, epoch)
+        metrics[epoch] = {k: float(v) for k, v in logger.mean.items()}
+        logger.reset()
+        put_dict(out, "sd{}".format(epoch), model.state_dict())
+    put_dict(out, "local0_sd2", local_model[0].state_dict())
+    out["metrics"] = np.array(json.dumps(metrics))
+    out["meta"] = np.array(json.dumps(meta_of(ns, {"epochs": 2})))
+    return out
+
+
 def run_case(case):
     kind, control, ns = setup(case)
-    fn = {"model": case_model, "mtal": case_mtal, "round": case_round}[kind]
+    fn = {"model": case_model, "mtal": case_mtal, "round": case_round, "joint": case_joint}[kind]
     out = fn(case, ns)
     path = os.path.join(HERE, case + ".npz")
     np.savez_compressed(path, **out)

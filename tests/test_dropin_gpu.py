@@ -169,3 +169,53 @@ def test_ml1m_shape_round_vs_oracle(dropin):
             assert rel_err(got["F"][t][k], ref["F"][t][k]) < (1e-6 if t == 0 else 5e-4), (t, k)
         r_got, r_ref = got["metrics"][t]["test/RMSE"], ref["metrics"][t]["test/RMSE"]
         assert abs(r_got - r_ref) <= 1e-4, (t, r_got, r_ref)
+
+
+@pytest.mark.parametrize("target_mode", ["explicit", "implicit"])
+@pytest.mark.parametrize("cold", ["none", "tail", "scattered"])
+@pytest.mark.parametrize("modes", [("optim", "optim"), ("optim", "constant"), ("constant", "optim")])
+def test_models_assist_is_differentiable(dropin, modes, cold, target_mode):
+    """models.assist as the reference uses it in its fit (closure at src/assist.py:121-126: forward, loss,
+    loss.backward() through the module): target, loss and the .grad of assist_rate / assist_weight against the
+    oracle's autograd form (oracle/models.py: assist_forward, reference src/models/assist.py:25-40), including the
+    cold-start branch (NaN in slot 0 -> softmax(w[1:]), rows moved to the end)."""
+    models, _, _ = dropin
+    from dmtcdr_b200.config import cfg, make_cfg
+    from oracle import models as om
+
+    make_cfg("ML100K_user_{}_ae_0_genre_assist_{}-0.3_{}".format(target_mode, modes[0], modes[1]), device="cuda", seed=0)
+    g = torch.Generator().manual_seed(3)
+    n, K, n_rate = 6001, cfg["num_organizations"], 53
+    out = torch.randn(n, K, generator=g)
+    if cold == "tail":
+        out[n * 2 // 3:, 0] = float("nan")
+    elif cold == "scattered":
+        out[torch.rand(n, generator=g) < 0.3, 0] = float("nan")
+    h = torch.randn(n, generator=g)
+    idx = torch.randint(0, n_rate - 3, (n,), generator=g)  # the last columns own no entry: their rate gradient is 0
+    t = torch.randn(n, generator=g) if target_mode == "explicit" else (torch.rand(n, generator=g) < 0.4).float()
+    rate0 = 0.3 + 0.1 * torch.randn(n_rate, generator=g)
+    w0 = torch.randn(K, generator=g)
+    module = models.assist(n_rate)
+    with torch.no_grad():
+        module.assist_rate.copy_(rate0)
+        module.assist_weight.copy_(w0)
+    module = module.to("cuda")
+    module.train(True)
+    inp = {"history": h.cuda(), "output": out.cuda(), "target": t.cuda(), "output_idx": idx.cuda()}
+    res = module(inp)
+    if any(p.requires_grad for p in module.parameters()):
+        res["loss"].backward()
+    rate = rate0.clone().requires_grad_(modes[0] == "optim")
+    w = w0.clone().requires_grad_(modes[1] == "optim")
+    pred, loss = om.assist_forward(rate, w, h, out, idx, t, target_mode)
+    loss.backward()
+    assert rel_err(res["target"].detach().cpu().numpy(), pred.detach().numpy()) < 2e-6
+    assert abs(float(res["loss"]) - float(loss)) <= 1e-5 * abs(float(loss))
+    if modes[0] == "optim":
+        assert rel_err(module.assist_rate.grad.cpu().numpy(), rate.grad.numpy()) < 2e-5
+    if modes[1] == "optim":
+        assert rel_err(module.assist_weight.grad.cpu().numpy(), w.grad.numpy()) < 2e-5
+    # a second evaluation of the same input dict (the L-BFGS closure) reuses the cached index work and agrees bit for bit
+    res2 = module(inp)
+    assert torch.equal(res2["target"], res["target"])

@@ -122,6 +122,30 @@ def test_org_blocks_cover_all_organizations():
         assert seen == list(range(K))
 
 
+def test_balanced_assignment_leaves_no_rank_idle():
+    """dist.assign_orgs: every organization owned once, counts differ by at most one (18 organizations on 8 ranks:
+    3,3,2,2,2,2,2,2 instead of the contiguous blocks' 3,3,3,3,3,3,0,0), heavier organizations spread first, and every
+    organization's row of the rank-blocked O_full lies inside its owner's block."""
+    from dmtcdr_b200 import dist as D
+
+    rng = np.random.default_rng(0)
+    for K, world in [(18, 1), (18, 2), (18, 4), (18, 8), (3, 8), (64, 8), (4, 3)]:
+        costs = rng.uniform(1, 10, K)
+        mine, chunk, org_row = D.assign_orgs(costs, world)
+        assert sorted(sum(mine, [])) == list(range(K))
+        counts = [len(m) for m in mine]
+        assert max(counts) - min(counts) <= 1 and chunk == max(counts)
+        assert len(set(org_row)) == K
+        for r, m in enumerate(mine):
+            assert m == sorted(m)
+            for j, k in enumerate(m):
+                assert org_row[k] == r * chunk + j
+        if K >= 2 * world:
+            loads = [sum(costs[k] for k in m) for m in mine]
+            assert max(loads) <= 1.5 * (sum(loads) / world)
+    assert D.assign_orgs([1.0] * 18, 8)[0] == D.assign_orgs([1.0] * 18, 8)[0]  # deterministic
+
+
 WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
@@ -130,17 +154,19 @@ import dmtcdr_b200
 from dmtcdr_b200 import dist as D
 rank, world, _ = D.init_from_env(backend="gloo")
 K, nnz = 5, 37
-orgs, chunk = D.org_block(K, world, rank)
+mine, chunk, org_row = D.assign_orgs([3.0, 1.0, 4.0, 1.0, 5.0], world)
+orgs = mine[rank]
 O = {{k: torch.zeros(chunk * world, nnz) for k in ("train", "test")}}
 for k, O_k in O.items():
     for o in orgs:
-        O_k[o] = torch.arange(nnz, dtype=torch.float32) + 100 * o + (1000 if k == "test" else 0)
+        O_k[org_row[o]] = torch.arange(nnz, dtype=torch.float32) + 100 * o + (1000 if k == "test" else 0)
 D.exchange_outputs(O, chunk, rank, world)
 for k, O_k in O.items():
     for o in range(K):
         want = torch.arange(nnz, dtype=torch.float32) + 100 * o + (1000 if k == "test" else 0)
-        assert torch.equal(O_k[o], want), (rank, k, o)
-    assert float(O_k[K:].abs().sum()) == 0.0
+        assert torch.equal(O_k[org_row[o]], want), (rank, k, o)
+    pad = [r for r in range(chunk * world) if r not in org_row]
+    assert float(O_k[pad].abs().sum()) == 0.0
 assert D.max_over_ranks(float(rank), "cpu") == float(world - 1)
 D.barrier()
 sys.stdout.write("rank%dok\n" % rank)

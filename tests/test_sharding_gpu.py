@@ -50,7 +50,7 @@ def test_two_emulated_ranks_match_one():
             r.combine()
         one.sync()
         for k in ("train", "test"):
-            assert torch.equal(one.state.O[k], ranks[0].state.O[k])
+            assert torch.equal(one.state.O_orgmajor(k), ranks[0].state.O_orgmajor(k))
             assert torch.equal(one.F[k], ranks[0].F[k]) and torch.equal(one.F[k], ranks[1].F[k])
             assert torch.isfinite(one.F[k]).all()
     for r in [one] + ranks:

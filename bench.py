@@ -62,6 +62,98 @@ def measured_tensor_peak():
     return 1590.0, "fallback (B200_PROFILING.md)"
 
 
+NCU_RAW = os.path.join(ROOT, "profiles", "r2_ncu_raw_fused.csv")
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+
+
+def ncu_per_kernel(path=NCU_RAW):
+    """Per-kernel averages parsed from the committed `ncu --set full` raw page (scripts/r2_prof.sh writes it):
+    {kernel: {'dram_bytes', 'l2_to_sm_bytes', 'us', 'regs', 'launches'}}. Raises when the file is missing: the
+    roofline block's `traffic` is measured evidence or nothing."""
+    import csv
+
+    if not os.path.exists(path):
+        raise FileNotFoundError("{} is missing: run scripts/r2_prof.sh under gpurun and commit its raw page".format(path))
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, key):
+        i = col[key]
+        return float(r[i].replace(",", "")) * _UNIT.get(units[i], 1.0)
+
+    acc = {}
+    for r in rows[2:]:
+        if len(r) != len(hdr):
+            continue
+        name = r[col["Kernel Name"]].split("(")[0].split("::")[-1]
+        a = acc.setdefault(name, {"dram_bytes": 0.0, "l2_to_sm_bytes": 0.0, "us": 0.0, "regs": 0, "launches": 0})
+        a["dram_bytes"] += val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+        a["l2_to_sm_bytes"] += val(r, "l1tex__m_xbar2l1tex_read_bytes.sum")
+        a["us"] += val(r, "gpu__time_duration.sum")
+        a["regs"] = int(float(r[col["launch__registers_per_thread"]]))
+        a["launches"] += 1
+    for a in acc.values():
+        for k in ("dram_bytes", "l2_to_sm_bytes", "us"):
+            a[k] /= a["launches"]
+    return acc
+
+
+# profile_step class -> kernel of csrc/fused.cu (bulk gather mode / register-load mode)
+CLASS_KERNEL = {"fwd_rows": ("ae_fwd_rows_kernel",) * 2, "decoder_loss_dz3": ("ae_dec_chunks_bulk_kernel", "ae_dec_chunks_kernel"),
+                "dw4_segments": ("ae_seg_chunks_bulk_kernel", "ae_seg_chunks_kernel"), "bwd_rows": ("ae_bwd_rows_kernel",) * 2,
+                "grad_phase": ("ae_grad_phase_kernel",) * 2, "grad_norm": ("norm_prepare_kernel",) * 2,
+                "clip_adam": ("adam_shadow_kernel",) * 2}
+
+
+def step_algorithmic_bytes(t_batch, d_batch, n_seg_t, n_seg_d, B, n_params, H1=256, H2=128):
+    """Compulsory bytes per launch of every kernel of the fused step (SURVEY.md section 8d's per-unit figures x the
+    units of one batch): gathered 1 KB rows count once per entry, dense operands once."""
+    act = 4 * B
+    wts = 4 * 2 * H1 * H2
+    return {
+        "fwd_rows": d_batch * (4 * H1 + 8) + wts + act * (H1 + H2 + H2 + H1),
+        "decoder_loss_dz3": t_batch * (4 * H1 + 16) + act * H1 * 2,
+        "dw4_segments": t_batch * (4 * H1 + 8) + n_seg_t * (4 * H1 + 4),
+        "bwd_rows": wts + act * (H1 + H2 + H1 + H2 + H1),
+        "grad_phase": d_batch * (4 * H1 + 8) + n_seg_d * 4 * H1 + act * (H1 + H2 + H2 + H1) + wts,
+        "grad_norm": 4 * n_params,
+        "clip_adam": 28 * n_params + 4 * n_params,
+    }
+
+
+def step_roofline(prof, bytes_by_class, gather_mode, hbm, peak_src):
+    """The roofline block: every kernel class of the step with its algorithmic bytes, CUDA-event time and the DRAM /
+    L2->SM traffic ncu measured for that kernel (parsed from profiles/, per launch); the headline entry is the class
+    with the longest launch."""
+    ncu = ncu_per_kernel()
+    idx = 0 if gather_mode == "bulk" else 1
+    classes = {}
+    for cls, ms in prof.items():
+        kern = CLASS_KERNEL[cls][idx]
+        n = ncu.get(kern)
+        b = bytes_by_class[cls]
+        ach = b / (ms * 1e-3) / 1e9
+        classes[cls] = {"kernel": kern, "ms_per_launch": ms, "algorithmic_bytes_per_launch": b, "achieved_GBps": ach,
+                        "frac_of_hbm_peak": ach / hbm,
+                        "traffic_dram_bytes": n["dram_bytes"] if n else None,
+                        "traffic_l2_to_sm_bytes": n["l2_to_sm_bytes"] if n else None,
+                        "ncu_us": n["us"] if n else None, "regs": n["regs"] if n else None}
+    dom = max(prof, key=prof.get)
+    d = classes[dom]
+    return {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved_GBps"], "peak": hbm, "unit": "GB/s",
+            "frac": d["frac_of_hbm_peak"], "traffic": d["traffic_dram_bytes"],
+            "traffic_source": "profiles/r2_ncu_raw_fused.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
+                              "of this kernel, per launch, parsed at bench time)",
+            "peak_source": peak_src, "ms_per_launch": d["ms_per_launch"],
+            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
+            "note": "ML1M-shape tables (W4 3.8 MB per organization) are L2-resident: the algorithmic bytes are served by "
+                    "L2 (traffic_l2_to_sm_bytes), DRAM traffic is far lower; hbm_case runs the same gather arithmetic "
+                    "on a shape L2 cannot hold",
+            "slowest_class": dom, "step_classes": classes, "step_sum_us": 1e3 * sum(prof.values())}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe's clocks line)."""
 
@@ -253,41 +345,42 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = visits / (ms_step / 1e3)
 
-    # ---- roofline of the dominant kernel, CUDA events on the launching stream (dmt_org_profile_step)
+    # ---- roofline: every kernel class of the step, CUDA events on the launching stream (dmt_org_profile_step), on the
+    #      grid the timed rounds use; ncu traffic per kernel parsed from profiles/ (fails loudly when absent)
     roof = None
     if rank == 0:
         org = rounds.my_orgs[0]
         eng = rounds.eng[org]
-        # the round runs the decoder chunk kernel on a reduced grid when many organizations share the GPU (a shorter
-        # round, a longer kernel): the kernel's own roofline is taken on its default grid, the in-round figure beside it
-        prof_round_grid = eng.h.profile_step(b=0, reps=20)
-        eng.h.set_decoder_blocks(0)
         prof = eng.h.profile_step(b=0, reps=20)
         n_params = eng.h.n_params
-        tl = eng.t_len
-        t_batch = float(np.mean([tl[b].sum() for b in E.fast_perm_batches(rounds.n_rows, 500)[:-1]]))
-        bytes_dec = t_batch * (4 * 256 + 16) + 500 * 256 * 4 * 2  # W4 row + col/target/grad per target, A3 in, dZ3 out
+        batches = E.fast_perm_batches(rounds.n_rows, 500)[:-1]
+        tl, dl = eng.t_len, eng.d_len
+        t_batch = float(np.mean([tl[b].sum() for b in batches]))
+        d_batch = float(np.mean([dl[b].sum() for b in batches]))
+        y_host = mats["train"][1]
+        d_host = mats["train"][0][:, data_split[org].numpy()].tocsr()
+        rows0 = np.sort(batches[0])
+        n_seg_t = int(np.unique(y_host[rows0].indices).size)
+        n_seg_d = int(np.unique(d_host[rows0].indices).size)
         hbm, peak_src = measured_peaks()
-        dom = max(prof, key=prof.get)
-        ach = bytes_dec / (prof["decoder_loss_dz3"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "ae_decoder_chunk_kernel<2> + ae_decoder_finish_kernel (decoder SDDMM + loss + dZ3)",
-                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": 5.14e6,
-                "traffic_source": "profiles/r1_ncu_raw_decoder_chunk.csv: dram__bytes_read.sum 5.14 MB + write 0 per launch",
-                "peak_source": peak_src, "ms_per_launch": prof["decoder_loss_dz3"],
-                "algorithmic_bytes_per_launch": bytes_dec,
-                "note": "ML1M-shape weights (W4 3.8 MB) are L2-resident: algorithmic bytes are served by L2, DRAM "
-                        "traffic is far lower (profiles/); see roofline_hbm_case for the same kernel on an HBM-bound shape",
-                "step_kernel_ms": prof, "slowest_class": dom,
-                "ms_per_launch_round_grid": prof_round_grid["decoder_loss_dz3"],
-                "round_grid_note": "decoder chunk grid in the timed rounds: {} blocks (default 296)".format(
-                    roundloop.decoder_blocks_for(len(rounds.my_orgs)) or 296),
-                "adam_GBps": n_params * 28 / (prof["clip_adam"] * 1e-3) / 1e9}
+        by_class = step_algorithmic_bytes(t_batch, d_batch, n_seg_t, n_seg_d, 500, n_params)
+        roof = step_roofline(prof, by_class, eng.h.gather_mode(), hbm, peak_src)
+        roof["grid_note"] = "profiled on the launch configuration of the timed rounds ({} organizations on this GPU)".format(
+            len(rounds.my_orgs))
+        # whole-round aggregate: compulsory bytes of one round / the CUDA-event time of the timed rounds
+        agg_bytes = E.bytes_per_round(rounds.K, rounds.state.y["train"].nnz, rounds.state.y["test"].nnz, rounds.n_rows,
+                                      [len(c) for c in rounds.cols], rounds.state.n_cols, args.local_epochs, 500)
+        roof["round_aggregate"] = {"algorithmic_bytes_per_round": agg_bytes, "ms_per_round": ms_step,
+                                   "achieved_GBps": agg_bytes / (ms_step * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": agg_bytes / (ms_step * 1e-3) / 1e9 / (hbm * world),
+                                   "note": "sum over all organizations and steps of the per-kernel compulsory bytes "
+                                           "(engine.bytes_per_round) over the measured round time, against N x the "
+                                           "measured HBM copy peak; most of it is served by L2 at this shape"}
         roof["hbm_case"] = hbm_bound_case(dev, hbm)
         # the decoder's other form (tcgen05 GEMMs, 3xTF32): same batch, same plan, per-class timings + D1 alone
         eng.set_decoder("tc")
         prof_tc = eng.h.profile_step(b=0, reps=20)
         eng.set_decoder(E.decoder_default() if eng.target.sorted else "gather")
-        eng.h.set_decoder_blocks(roundloop.decoder_blocks_for(len(rounds.my_orgs)))
         roof["tc_decoder"] = tc_decoder_case(rounds.state.y["train"], dev, prof, prof_tc)
 
     # ---- end to end through the drop-in API with host buffers (single-process API: measured on rank 0's GPU)
@@ -450,6 +543,8 @@ def tc_decoder_case(y_csr, dev, prof_gather, prof_tc):
                                   "18 % (D3) of peak sustained active",
             "step_kernel_ms_gather": {k: prof_gather[k] for k in ("decoder_loss_dz3", "dw4_segments")},
             "step_kernel_ms_tc": {k: prof_tc[k] for k in ("decoder_loss_dz3", "dw4_segments")},
+            "verdict": "measured negative at all three BASELINE shapes (other_configs.*.tc_vs_gather): the gather form "
+                       "is the engine default, the tensor-core form stays opt-in (DMT_DECODER=tc)",
             "note": "latency-bound at this size (116 CTAs x 8 k-chunks); the gather form stays the engine default at "
                     "ML1M shape (DESIGN.md section 5)"}
 
@@ -590,6 +685,28 @@ def run_config_block(control, data_name, dev, n_rounds=2, n_warm=2, local_epochs
     bytes_dec = t_batch * (4 * 256 + 16) + min(bs, R.n_rows) * 256 * 4 * 2
     hbm, _ = measured_peaks()
     metrics = R.evaluate("test")
+    # the decoder's tensor-core form on the same batch and plan (measured per BASELINE shape)
+    tc_vs = None
+    if eng.target.sorted:
+        try:
+            eng.set_decoder("tc")
+            prof_tc = eng.h.profile_step(b=0, reps=10)
+            eng.set_decoder("gather")
+            keys = ("decoder_loss_dz3", "dw4_segments")
+            tc_vs = {"gather_ms": {k: prof[k] for k in keys}, "tc_3xTF32_ms": {k: prof_tc[k] for k in keys},
+                     "tc_over_gather": sum(prof_tc[k] for k in keys) / sum(prof[k] for k in keys),
+                     "target_density": n_tr / (R.n_rows * R.state.n_cols)}
+        except Exception as e:
+            tc_vs = {"error": "{}: {}".format(type(e).__name__, e)}
+    n_params = eng.h.n_params
+    d_batch = float(eng.d_len.sum()) / nb
+    by_class = step_algorithmic_bytes(t_batch, d_batch, min(R.state.n_cols, int(t_batch)), min(eng.n_enc, int(d_batch)),
+                                      min(bs, R.n_rows), n_params)
+    classes = {k: {"ms_per_launch": v, "algorithmic_bytes_per_launch": by_class[k],
+                   "achieved_GBps": by_class[k] / (v * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": by_class[k] / (v * 1e-3) / 1e9 / hbm} for k, v in prof.items() if k in by_class}
+    agg_bytes = E.bytes_per_round(R.K, n_tr, R.state.y["test"].nnz, R.n_rows, [len(c) for c in R.cols], R.state.n_cols,
+                                  local_epochs, bs)
     out = {"control_name": control,
            "workload": "{}-shape (synthetic, SURVEY.md 8d): {} x {}, {} train / {} test entries, {} organizations, "
                        "batch {} rows, {} local epochs".format(data_name, R.n_rows, R.state.n_cols, n_tr,
@@ -601,6 +718,10 @@ def run_config_block(control, data_name, dev, n_rounds=2, n_warm=2, local_epochs
            "decoder_roofline": {"algorithmic_bytes_per_launch": bytes_dec, "ms_per_launch": prof["decoder_loss_dz3"],
                                 "achieved_GBps": bytes_dec / (prof["decoder_loss_dz3"] * 1e-3) / 1e9,
                                 "frac_of_hbm_peak": bytes_dec / (prof["decoder_loss_dz3"] * 1e-3) / 1e9 / hbm},
+           "step_classes": classes,
+           "round_aggregate": {"algorithmic_bytes_per_round": agg_bytes, "achieved_GBps": agg_bytes / (ms * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": agg_bytes / (ms * 1e-3) / 1e9 / hbm},
+           "tc_vs_gather": tc_vs,
            "test_metrics_after_{}_rounds".format(n_warm + n_rounds): metrics}
     R.close()
     del R

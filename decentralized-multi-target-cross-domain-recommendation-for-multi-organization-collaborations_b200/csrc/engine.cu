@@ -78,6 +78,8 @@ struct dmt_org {
     // tensor-core decoder (decoder_tc.cu)
     int dec_mode, dec_passes;
     int dec_blocks;  // grid of the decoder chunk kernel (0: two per SM), dmt_org_set_decoder_blocks
+    int gather;      // fused step: 1 = weight / activation rows through bulk-copy rings (bulk.cuh), 0 = plain loads
+    int bulk_blocks; // grid of the bulk decoder kernel (0: five per SM)
     int fanout;  // 1: the backward pass of a step is enqueued as parallel branches (dmt_org_set_fanout)
     float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
     // tables of per-row CSR windows at 128-column tile borders, one per target CSR seen (train targets, predict splits)
@@ -379,7 +381,7 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     if (WANT(K_DEC)) {
         FusedDec d{br, o->dec_meta, o->t_batch_chunk, o->pt.batch_cnt, o->t_indices, o->t_val, o->t_inv_perm,
                    o->a3, W4, b4, o->g_sorted, o->dz3, o->loss_rows, o->dz_part, o->loss_part, o->row_cnt};
-        if ((rc = launch_fused_dec(d, o->dec_blocks, st))) return rc;
+        if ((rc = launch_fused_dec(d, o->gather ? o->bulk_blocks : o->dec_blocks, o->gather, st))) return rc;
     }
     // dW4 / db4 only has to be complete before the norm: it runs as a parallel branch of the captured step graph next
     // to the critical path backward rows -> dW3 / dW2 / dW1 (profiling keeps everything on the main stream)
@@ -392,7 +394,7 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
         }
         FusedSeg s{o->t_seg_meta, o->pt.batch_chunk_off, o->t_row_sorted, o->g_sorted, o->pt.part, o->pt.part_bias,
                    o->t_seg_cnt, o->active, b};
-        if ((rc = launch_fused_seg_chunks(s, o->a3, G + o->oW4, G + o->ob4, o->n_dec * 2, sA))) return rc;
+        if ((rc = launch_fused_seg_chunks(s, o->a3, G + o->oW4, G + o->ob4, o->n_dec * 2, o->gather, sA))) return rc;
     }
     if (WANT(K_SEG_W1)) {
         FusedBwd w{br, o->pt.len, o->dz3, W3, W2, o->a1, o->a2, o->dz2, o->dz1, o->part_db, drop};
@@ -682,6 +684,10 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
     {
         const char* env = getenv("DMT_DEC_BLOCKS");
         o->dec_blocks = env ? atoi(env) : 0;
+        env = getenv("DMT_GATHER");
+        o->gather = (env && strcmp(env, "bulk") == 0) ? 1 : 0;  // measured: per-row bulk copies are slower
+        env = getenv("DMT_BULK_BLOCKS");
+        o->bulk_blocks = env ? atoi(env) : 0;
     }
     A(dalloc(&o->tc_scratch, decoder_tc_scratch_floats(batch_rows, n_dec, H1)));
     A(dalloc(&o->gbuf, t_cap)); A(dalloc(&o->dval_ord, d_cap)); A(dalloc(&o->row_batch, o->rows_cap + 1));
@@ -754,6 +760,15 @@ int dmt_org_set_decoder_blocks(dmt_org_t* o, int blocks) {
     o->dec_blocks = blocks;
     return 0;
 }
+
+int dmt_org_set_gather_mode(dmt_org_t* o, int mode) {
+    DMT_REQUIRE(o && (mode == 0 || mode == 1), "dmt_org_set_gather_mode: bad argument");
+    if (o->gather != mode) drop_graph(o);  // the kernels are baked into the captured graph
+    o->gather = mode;
+    return 0;
+}
+
+int dmt_org_gather_mode(const dmt_org_t* o) { return o ? o->gather : 0; }
 
 int dmt_org_set_fanout(dmt_org_t* o, int on) {
     DMT_REQUIRE(o, "dmt_org_set_fanout: null");

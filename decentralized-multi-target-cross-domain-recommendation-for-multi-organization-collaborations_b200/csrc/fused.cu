@@ -21,6 +21,7 @@
 //
 // All kernels read their batch bounds from device memory (BatchRef), so the epoch graph is replayable. fp32 FFMA
 // throughout (the parity bar is 1e-5 relative on the loss). Shapes: H1 = 256, H2 = 128 (src/utils.py:166-171).
+#include "bulk.cuh"
 #include "kernels.cuh"
 
 namespace dmt {
@@ -305,6 +306,126 @@ __device__ __forceinline__ void dec_chunks_body(const FusedDec& p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 2' decoder, bulk form
+// Same contract as dec_chunks_body; the W4 rows of a chunk travel through warp-private shared-memory rings filled by
+// the bulk-copy engine (bulk.cuh) instead of through registers. Four warps per block share a chunk's targets evenly;
+// ~50 registers per thread and 41 KB of shared memory per block let five blocks live on one SM, each with up to
+// 32 KB of weight rows in flight.
+constexpr int kBulkWarps = 4;
+constexpr int kBulkSlots = 8;
+
+__device__ __forceinline__ void dec_chunks_bulk_body(const FusedDec& p) {
+    constexpr int H = H1c;
+    __shared__ __align__(128) float ring[kBulkWarps][kBulkSlots][H];
+    __shared__ __align__(16) float s_acc[2][kBulkWarps][H];
+    __shared__ float s_loss[2][kBulkWarps];
+    __shared__ __align__(8) uint64_t bars[kBulkWarps][kBulkSlots];
+    __shared__ int s_last;
+    int lo, hi;
+    if (!batch_range(p.br, lo, hi)) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c_lo = p.batch_chunk_off[p.br.b], c_hi = p.batch_chunk_off[p.br.b + 1];
+    if (c_lo + (int)blockIdx.x >= c_hi) return;
+    bulk::WarpRing<kBulkSlots> rg = bulk::ring_setup<kBulkSlots>(&ring[wid][0][0], &bars[wid][0], lane);
+    __syncthreads();
+    const float inv_n = 1.f / (float)p.n_targets[p.br.b];
+    int buf = 0;
+    for (int c = c_lo + blockIdx.x; c < c_hi; c += gridDim.x, buf ^= 1) {
+        const int4 mt = p.meta[c];
+        const int jl = mt.x, e0 = mt.y, out0 = mt.z;
+        const int n_tg = mt.w & 0xff;               // 1..128 targets in this chunk
+        const int k = (mt.w >> 8) & 0xfff;          // chunk index inside the row
+        const int n_ch = (mt.w >> 20) & 0xfff;      // chunks of the row
+        const float* a_row = p.A3 + (int64_t)jl * H;
+        const int per = (n_tg + kBulkWarps - 1) / kBulkWarps;  // <= 32 targets per warp
+        const int off = wid * per;
+        const int cnt = max(0, min(per, n_tg - off));
+        int c_l = 0, pos_l = 0;
+        float y_l = 0.f, b_l = 0.f;
+        if (lane < cnt) {
+            c_l = p.t_indices[e0 + off + lane];
+            y_l = p.target[e0 + off + lane];
+            pos_l = p.inv_perm[out0 + off + lane];
+            b_l = p.b4[c_l];
+        }
+        const float4 a0 = ld4(a_row + lane * 4), a1 = ld4(a_row + 128 + lane * 4);
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        float o_l = 0.f;
+        bulk::gather_rows(rg, p.W4, c_l, cnt, lane, [&](int t0, int nv, const float4(&w)[4][2]) {
+            float d[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[q] = dot4(a0, w[q][0]) + dot4(a1, w[q][1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[q] = warp_sum(d[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < nv) {
+                    const int tq = t0 + q;
+                    const float o = d[q] + __shfl_sync(0xffffffffu, b_l, tq);
+                    const float y = __shfl_sync(0xffffffffu, y_l, tq);
+                    if (lane == tq) o_l = o;
+                    const float gq = loss_grad(DMT_LOSS_MSE, o, y) * inv_n;
+                    fma4(acc0, gq, w[q][0]);
+                    fma4(acc1, gq, w[q][1]);
+                }
+            }
+        });
+        float loss_acc = 0.f;
+        if (lane < cnt) {
+            p.g_sorted[pos_l] = loss_grad(DMT_LOSS_MSE, o_l, y_l) * inv_n;
+            loss_acc = loss_value(DMT_LOSS_MSE, o_l, y_l);
+        }
+        st4(&s_acc[buf][wid][lane * 4], acc0);
+        st4(&s_acc[buf][wid][128 + lane * 4], acc1);
+        loss_acc = warp_sum(loss_acc);
+        if (lane == 0) s_loss[buf][wid] = loss_acc;
+        __syncthreads();
+        const int h = threadIdx.x * 2;  // 128 threads x 2 hidden units
+        float2 s = make_float2(0.f, 0.f);
+        float l = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < kBulkWarps; ++w4) {
+            const float2 v = *reinterpret_cast<const float2*>(&s_acc[buf][w4][h]);
+            s.x += v.x;
+            s.y += v.y;
+            l += s_loss[buf][w4];
+        }
+        if (n_ch == 1) {
+            const float2 av = *reinterpret_cast<const float2*>(a_row + h);
+            *reinterpret_cast<float2*>(p.dZ3 + (int64_t)jl * H + h) =
+                make_float2(s.x * (1.f - av.x * av.x), s.y * (1.f - av.y * av.y));
+            if (threadIdx.x == 0) p.loss_rows[jl] = l;
+        } else {
+            const int64_t slot = c - c_lo;
+            *reinterpret_cast<float2*>(p.dz_part + slot * H + h) = s;
+            if (threadIdx.x == 0) p.loss_part[slot] = l;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(&p.row_cnt[jl], 1) == n_ch - 1);
+            __syncthreads();
+            if (s_last) {  // block-uniform: this chunk arrived last, add the row's partials in chunk order
+                __threadfence();
+                const int64_t first = slot - k;
+                float2 tot = make_float2(0.f, 0.f);
+                for (int q = 0; q < n_ch; ++q) {
+                    const float2 v = __ldcg(reinterpret_cast<const float2*>(p.dz_part + (first + q) * H + h));
+                    tot.x += v.x;
+                    tot.y += v.y;
+                }
+                const float2 av = *reinterpret_cast<const float2*>(a_row + h);
+                *reinterpret_cast<float2*>(p.dZ3 + (int64_t)jl * H + h) =
+                    make_float2(tot.x * (1.f - av.x * av.x), tot.y * (1.f - av.y * av.y));
+                if (threadIdx.x == 0) {
+                    float lt = 0.f;
+                    for (int q = 0; q < n_ch; ++q) lt += __ldcg(p.loss_part + first + q);
+                    p.loss_rows[jl] = lt;
+                    p.row_cnt[jl] = 0;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ 3a backward rows
 template <int R>
 __device__ __forceinline__ void bwd_rows_body(const FusedBwd& p, int cta) {
@@ -460,6 +581,75 @@ __device__ __forceinline__ void seg_chunks_body(const FusedSeg& s, const float* 
     }
 }
 
+// 3b' / 4c': the segmented reductions with the source rows streamed through a warp's bulk-copy ring (bulk.cuh)
+__device__ __forceinline__ void seg_chunks_bulk_body(const FusedSeg& s, const float* __restrict__ src,
+                                                     float* __restrict__ grad, float* __restrict__ bias_grad,
+                                                     bulk::WarpRing<kBulkSlots>& rg, int warp, int n_warps) {
+    constexpr int W = H1c;
+    const int lane = threadIdx.x & 31;
+    const int c_lo = s.batch_chunk_off[s.b], c_hi = s.batch_chunk_off[s.b + 1];
+    for (int c = c_lo + warp; c < c_hi; c += n_warps) {
+        const int4 mt = s.meta[c];
+        const int e0 = mt.x, e1 = mt.y, row_out = mt.z;
+        const int k = mt.w & 0xffff, n_ch = mt.w >> 16;
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        float bsum = 0.f;
+        for (int eb = e0; eb < e1; eb += 32) {
+            const int e = eb + lane;
+            float c_l = 0.f;
+            int r_l = 0;
+            if (e < e1) {
+                c_l = s.coef_sorted[e];
+                r_l = s.row_sorted[e];
+            }
+            bsum += c_l;
+            bulk::gather_rows(rg, src, r_l, min(32, e1 - eb), lane, [&](int t0, int nv, const float4(&x)[4][2]) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < nv) {
+                        const float cq = __shfl_sync(0xffffffffu, c_l, t0 + q);
+                        fma4(acc0, cq, x[q][0]);
+                        fma4(acc1, cq, x[q][1]);
+                    }
+                }
+            });
+        }
+        bsum = warp_sum(bsum);
+        if (n_ch == 1) {
+            st4(grad + (int64_t)row_out * W + lane * 4, acc0);
+            st4(grad + (int64_t)row_out * W + 128 + lane * 4, acc1);
+            if (bias_grad != nullptr && lane == 0) bias_grad[row_out] = bsum;
+        } else {
+            const int64_t slot = c - c_lo;
+            st4(s.part + slot * W + lane * 4, acc0);
+            st4(s.part + slot * W + 128 + lane * 4, acc1);
+            if (lane == 0) s.part_bias[slot] = bsum;
+            __threadfence();
+            __syncwarp();
+            const int64_t first = slot - k;
+            int ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&s.cnt[first], 1);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            if (ticket == n_ch - 1) {  // last chunk of the segment: add the partial rows in chunk order
+                __threadfence();
+                float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+                float bt = 0.f;
+                for (int q = 0; q < n_ch; ++q) {
+                    add4(t0, ldcg4(s.part + (first + q) * W + lane * 4));
+                    add4(t1, ldcg4(s.part + (first + q) * W + 128 + lane * 4));
+                    if (lane == 0) bt += __ldcg(s.part_bias + first + q);
+                }
+                st4(grad + (int64_t)row_out * W + lane * 4, t0);
+                st4(grad + (int64_t)row_out * W + 128 + lane * 4, t1);
+                if (lane == 0) {
+                    if (bias_grad != nullptr) bias_grad[row_out] = bt;
+                    s.cnt[first] = 0;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ 4a dW3 / dW2 tiles
 // out[n][k] = sum_r Dn[r][n] * Xk[r][k] over the batch rows r (both operands row-major with r outermost: coalesced).
 // 64 x 64 output tile per block, one slice of <= kDwSlice rows; 256 threads x (4 x 4) outputs.
@@ -560,6 +750,19 @@ __device__ __forceinline__ void db_finish_body(const FusedGrad& p) {
 __global__ void __launch_bounds__(256) ae_fwd_rows_kernel(FusedFwd p) { fwd_rows_body<kFusedRows>(p, blockIdx.x); }
 
 __global__ void __launch_bounds__(256) ae_dec_chunks_kernel(FusedDec p) { dec_chunks_body(p); }
+
+__global__ void __launch_bounds__(kBulkWarps * 32) ae_dec_chunks_bulk_kernel(FusedDec p) { dec_chunks_bulk_body(p); }
+
+__global__ void __launch_bounds__(kBulkWarps * 32) ae_seg_chunks_bulk_kernel(FusedSeg s, const float* src, float* grad,
+                                                                             float* bias_grad) {
+    __shared__ __align__(128) float ring[kBulkWarps][kBulkSlots][H1c];
+    __shared__ __align__(8) uint64_t bars[kBulkWarps][kBulkSlots];
+    if (s.active != nullptr && s.active[s.b] == 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bulk::WarpRing<kBulkSlots> rg = bulk::ring_setup<kBulkSlots>(&ring[wid][0][0], &bars[wid][0], lane);
+    __syncthreads();
+    seg_chunks_bulk_body(s, src, grad, bias_grad, rg, blockIdx.x * kBulkWarps + wid, gridDim.x * kBulkWarps);
+}
 
 // 3a and 3b are separate kernels on parallel branches of the step graph: the row kernel keeps 64 weights per thread in
 // flight (~100 registers), the segment kernel needs 64 registers and four resident blocks per SM.
@@ -762,7 +965,13 @@ int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st) {
     return 0;
 }
 
-int launch_fused_dec(const FusedDec& p, int blocks_hint, cudaStream_t st) {
+int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st) {
+    if (gather == 1) {  // bulk-copy rings: five 128-thread blocks per SM
+        const int blocks = blocks_hint > 0 ? blocks_hint : kNumSMs * 5;
+        ae_dec_chunks_bulk_kernel<<<blocks, kBulkWarps * 32, 0, st>>>(p);
+        DMT_LAUNCH_CHECK();
+        return 0;
+    }
     const int blocks = blocks_hint > 0 ? blocks_hint : kNumSMs * 2;
     ae_dec_chunks_kernel<<<blocks, 256, 0, st>>>(p);
     DMT_LAUNCH_CHECK();
@@ -777,7 +986,15 @@ int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st) {
 }
 
 int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, float* bias_grad, int n_chunk_max,
-                            cudaStream_t st) {
+                            int gather, cudaStream_t st) {
+    if (gather == 1) {
+        int blocks = (n_chunk_max + kBulkWarps - 1) / kBulkWarps;
+        if (blocks > kNumSMs * 6) blocks = kNumSMs * 6;
+        if (blocks < 1) blocks = 1;
+        ae_seg_chunks_bulk_kernel<<<blocks, kBulkWarps * 32, 0, st>>>(s, src, grad, bias_grad);
+        DMT_LAUNCH_CHECK();
+        return 0;
+    }
     int seg_blocks = (n_chunk_max + 7) / 8;
     if (seg_blocks > kNumSMs * 2) seg_blocks = kNumSMs * 2;
     if (seg_blocks < 1) seg_blocks = 1;

@@ -224,10 +224,11 @@ struct FusedPlanArgs {
     FusedPlanSide t, d;
 };
 int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st);
-int launch_fused_dec(const FusedDec& p, int blocks_hint, cudaStream_t st);
+// gather: 0 = rows through registers (plain loads), 1 = rows through shared-memory rings (bulk copies, bulk.cuh)
+int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st);
 int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st);
 int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, float* bias_grad, int n_chunk_max,
-                            cudaStream_t st);
+                            int gather, cudaStream_t st);
 int launch_fused_grad_phase(const FusedGrad& p, const FusedSeg& s, const float* src, float* grad, int n_chunk_max,
                             cudaStream_t st);
 int launch_norm_prepare(const float* g, int64_t n, float* partial, AdamScalars* sc, int* step_dev,

@@ -85,6 +85,8 @@ def _declare(lib):
         "dmt_org_set_decoder_mode": (I, [P, I, I]),
         "dmt_org_set_fanout": (I, [P, I]),
         "dmt_org_set_decoder_blocks": (I, [P, I]),
+        "dmt_org_set_gather_mode": (I, [P, I]),
+        "dmt_org_gather_mode": (I, [P]),
         "dmt_org_set_step_mode": (I, [P, I]),
         "dmt_org_step_mode": (I, [P]),
         "dmt_ae_encoder_fwd": (I, [P, I, P, P, P, P, P, I, P, P]),
@@ -559,6 +561,14 @@ class Org:
     def set_decoder_blocks(self, blocks):
         """Grid of the decoder chunk kernel (0: two blocks per SM); fewer blocks pay with many organizations per GPU."""
         check(self._lib.dmt_org_set_decoder_blocks(self.h, int(blocks)), "dmt_org_set_decoder_blocks")
+
+    def set_gather_mode(self, mode):
+        """'ldg' (register loads, default) or 'bulk' (one cp.async.bulk copy per row into shared-memory rings,
+        csrc/bulk.cuh; measured slower, kept as the parity-tested alternative)."""
+        check(self._lib.dmt_org_set_gather_mode(self.h, {"ldg": 0, "bulk": 1}[mode]), "dmt_org_set_gather_mode")
+
+    def gather_mode(self):
+        return "bulk" if self._lib.dmt_org_gather_mode(self.h) == 1 else "ldg"
 
     def set_step_mode(self, mode):
         """'fused' (six launches per batch, csrc/fused.cu) or 'classic' (one kernel per layer / reduction)."""

@@ -271,6 +271,14 @@ int dmt_org_set_fanout(dmt_org_t* org, int on);
  * (148), because the kernel's register footprint then leaves room for the other organizations' kernels (measured at
  * ML1M shape, 18 organizations: 214.7 -> 205.6 ms per round while the kernel itself goes from 23.6 to 32.9 us). */
 int dmt_org_set_decoder_blocks(dmt_org_t* org, int blocks);
+/* How the gather kernels of the fused step (decoder SDDMM of src/models/ae.py:135-142 and the dW4 segments of its
+ * backward) bring their 1 KB weight / activation rows to the SM. mode 0 (default): 128-bit loads into registers,
+ * software-pipelined in groups of four rows. mode 1 (DMT_GATHER=bulk): one cp.async.bulk copy per row into
+ * warp-private shared-memory rings completed on mbarriers (csrc/bulk.cuh); parity-tested, measured SLOWER at every
+ * grid (decoder 28-45 us against 23 us at ML1M shape: the copy engine's per-operation cost dominates at 1 KB), kept
+ * as the measured alternative. Same sums in a different fixed order. */
+int dmt_org_set_gather_mode(dmt_org_t* org, int mode);
+int dmt_org_gather_mode(const dmt_org_t* org);
 /* How one iteration of the batch loop (src/organization.py:149-162) is cut into launches. mode 1 (default whenever
  * H1 = 256, H2 = 128, batch_rows <= 512 and decoder mode 0): the fused step of csrc/fused.cu — six dependent launches
  * (row-local forward, decoder chunks, {row-local backward | dW4 segments}, {dW3/dW2 tiles | bias gradients | dW1

@@ -75,7 +75,7 @@ def unflat_params(flat, n_enc, n_dec, H1=256, H2=128):
     return out
 
 
-@pytest.mark.parametrize("decoder", ["gather", "tc"])
+@pytest.mark.parametrize("decoder", ["gather", "gather_bulk", "tc"])
 @pytest.mark.parametrize("seed,bs,n_rows,n_dec", [(0, 50, 130, 100), (1, 64, 130, 100), (2, 150, 400, 300)])
 def test_train_epochs_and_predict(nat, seed, bs, n_rows, n_dec, decoder):
     rng = np.random.default_rng(seed)
@@ -111,6 +111,10 @@ def test_train_epochs_and_predict(nat, seed, bs, n_rows, n_dec, decoder):
     d_csr = (cu(D.indptr, torch.int32), cu(D.indices, torch.int32), cu(D.data))
     t_csr = (cu(T.indptr, torch.int32), cu(T.indices, torch.int32))
     org = nat.Org(n_rows, n_enc, n_dec, 256, 128, d_csr, t_csr, bs, 0)
+    # "gather": rows through registers (default); "gather_bulk": through bulk-copy shared-memory rings (csrc/bulk.cuh)
+    org.set_gather_mode("bulk" if decoder == "gather_bulk" else "ldg")
+    assert org.gather_mode() == ("bulk" if decoder == "gather_bulk" else "ldg")
+    decoder = "gather" if decoder == "gather_bulk" else decoder
     org.set_decoder_mode(decoder)  # "tc": the decoder's last layer on tcgen05 (3xTF32), same tolerances
     org.wait_current()
     org.set_params(flat_params(p0).cuda())
@@ -190,7 +194,7 @@ def chunk_census(T, batches, dec_chunk=128, seg_chunk=64):
 
 
 @pytest.mark.parametrize("mode", ["epoch", "epoch_fanout", "round"])
-@pytest.mark.parametrize("decoder", ["gather", "gather_classic", "tc"])
+@pytest.mark.parametrize("decoder", ["gather", "gather_bulk", "gather_classic", "tc"])
 @pytest.mark.parametrize("shape", ["ml1m_batch", "zipf_wide"])
 def test_train_benchmark_shape(nat, shape, decoder, mode):
     """The paths the benchmark runs (VERDICT r1 'parity hole'): 500-row batches over 3706 target columns with rows of
@@ -224,8 +228,12 @@ def test_train_benchmark_shape(nat, shape, decoder, mode):
     d_csr = (cu(D.indptr, torch.int32), cu(D.indices, torch.int32), cu(D.data))
     t_csr = (cu(T.indptr, torch.int32), cu(T.indices, torch.int32))
     org = nat.Org(n_rows, n_enc, n_dec, 256, 128, d_csr, t_csr, bs, 0, plan_epochs=n_epochs if mode == "round" else 1)
-    # "gather": the fused six-launch step (csrc/fused.cu, the default); "gather_classic": one kernel per layer
-    want_fused = decoder == "gather"
+    # "gather": the fused six-launch step (csrc/fused.cu, the default); "gather_bulk": the same step with the gathered
+    # rows travelling through bulk-copy rings (csrc/bulk.cuh); "gather_classic": one kernel per layer
+    want_fused = decoder in ("gather", "gather_bulk")
+    org.set_gather_mode("bulk" if decoder == "gather_bulk" else "ldg")
+    if decoder == "gather_bulk":
+        decoder = "gather"
     if decoder == "gather_classic":
         org.set_step_mode("classic")
         decoder = "gather"

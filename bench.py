@@ -387,6 +387,12 @@ def run_ours(args):
     e2e = run_e2e(args, data, rank, world, dev)
 
     mf = run_mf_joint(data, dev) if (rank == 0 and world == 1) else None
+    nmf = None
+    if rank == 0 and world == 1 and args.configs != "none":
+        try:
+            nmf = run_nmf_alone(data, dev)
+        except Exception as e:
+            nmf = {"error": "{}: {}".format(type(e).__name__, e)}
     # the other BASELINE.json configurations, as extra blocks of the line (N=1 only; each with its own CPU leg)
     more = None
     if rank == 0 and world == 1 and args.configs != "none":
@@ -431,7 +437,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2: per-round working set (18 x 17 MB parameters+moments, "
                                     "2 x 72 MB prediction matrices, plans) exceeds 126 MB"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
-            "cpu_baseline": cpu, "mf_joint": mf, "other_configs": more}
+            "cpu_baseline": cpu, "mf_joint": mf, "nmf_alone": nmf, "other_configs": more}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
@@ -632,6 +638,95 @@ def run_mf_joint(data, dev, epochs=3):
             "cpu_baseline": {"value": nnz / cpu_sec, "unit": "ratings/s", "cores": os.cpu_count() or 1, "kind": "port",
                              "sample": "one joint-MF epoch with the oracle port ({:.1f} s)".format(cpu_sec)}}
 
+
+def run_nmf_alone(data, dev, epochs=2):
+    """Config 2 (`ML1M_item_implicit_nmf_0_random-8_alone`; the literal `nmf_1` control crashes in the reference on
+    ML1M-shape data, SURVEY.md section 8c, so `info=0` is what is timed): 8 organizations, each training its own NCF
+    (drop-in `models.nmf`: embedding gather + concat kernel, FFMA tower, GMF product + affine + BCE fused) on its block of
+    user columns with the driver-owned clip_grad_norm_ + torch.optim.Adam (reference src/train_recsys_alone.py:130-147),
+    batches of 500 items resident on the device. ratings/s over all organizations + the oracle port on the host cores for
+    one organization-epoch."""
+    import dmtcdr_b200
+    from dmtcdr_b200 import runner
+    from dmtcdr_b200.config import make_cfg
+
+    control = "ML1M_item_implicit_nmf_0_random-8_alone"
+    cfg = make_cfg(control, device="cuda", seed=0)
+    models, _, _ = dmtcdr_b200.use_dropin()
+    torch.manual_seed(0)
+    dataset = runner.fetch_dataset(data)
+    runner.process_dataset(dataset)
+    split = runner.split_dataset(dataset)
+    org_ds = runner.make_split_dataset(dataset, split)
+    K = len(org_ds)
+    bs = cfg["nmf"]["batch_size"]["train"] if "batch_size" in cfg["nmf"] else 500
+    org_models, opts = [], []
+    for k in range(K):
+        ds = org_ds[k]["train"]
+        m = models.nmf(ds.num_users["data"], ds.num_items["data"]).to(dev)
+        m.train(True)
+        org_models.append(m)
+        opts.append(torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=5e-4))
+    g = torch.Generator().manual_seed(0)
+
+    def epoch_batches(k):
+        ds = org_ds[k]["train"]
+        perm = torch.randperm(len(ds), generator=g).numpy()
+        out = []
+        for s0 in range(0, len(ds), bs):
+            b = runner.pair_batch(ds, perm[s0:s0 + bs])
+            if len(b[cfg["data_mode"]]) > 0:
+                out.append({kk: v.to(dev) for kk, v in b.items()})
+        return out
+
+    def run_epoch(k, batches):
+        loss = None
+        for b in batches:
+            opts[k].zero_grad()
+            out = org_models[k](b)
+            out["loss"].backward()
+            torch.nn.utils.clip_grad_norm_(org_models[k].parameters(), 1)
+            opts[k].step()
+            loss = out["loss"]
+        return loss
+
+    for k in range(K):
+        run_epoch(k, epoch_batches(k))  # warm-up
+    sets = [[epoch_batches(k) for k in range(K)] for _ in range(epochs)]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for per_org in sets:
+        for k in range(K):
+            loss = run_epoch(k, per_org[k])
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3 / epochs
+    nnz = sum(org_ds[k]["train"].data.nnz for k in range(K))
+    n_steps = sum(len(per_org[k]) for per_org in sets[:1] for k in range(K))
+    # CPU: the oracle port, organization 0, one epoch
+    from oracle import models as om
+    from oracle import train as otrain
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {kk: v.detach().cpu() for kk, v in org_models[0].state_dict().items()}
+    oopt = otrain.Adam(sd)
+    ds0 = org_ds[0]["train"]
+    perm = torch.randperm(len(ds0), generator=g).numpy()
+    t0 = time.perf_counter()
+    for s0 in range(0, len(ds0), bs):
+        cb = runner.pair_batch(ds0, perm[s0:s0 + bs])
+        if len(cb[cfg["data_mode"]]) > 0:
+            otrain.train_step(oopt, lambda p: om.pair_forward("nmf", p, cb, "implicit", True))
+    cpu_sec = time.perf_counter() - t0
+    return {"workload": "{}: {} organizations (random user blocks), {} train ratings in total, batches of {} items, "
+                        "{} optimizer steps per epoch over all organizations".format(control, K, nnz, bs, n_steps),
+            "value": nnz / sec, "unit": "ratings/s", "ms_per_epoch_all_orgs": 1e3 * sec,
+            "us_per_step": 1e6 * sec / max(n_steps, 1), "last_loss": float(loss),
+            "note": "module-level path: the driver owns backward / clip / Adam, so every step pays torch's eager "
+                    "dispatch around the kernels (DESIGN.md: host-bound at this size)",
+            "cpu_baseline": {"value": ds0.data.nnz / cpu_sec, "unit": "ratings/s", "cores": os.cpu_count() or 1,
+                             "kind": "port", "sample": "organization 0, one epoch with the oracle port ({:.1f} s)".format(
+                                 cpu_sec)}}
 
 
 def run_config_block(control, data_name, dev, n_rounds=2, n_warm=2, local_epochs=20, cpu_leg=True):

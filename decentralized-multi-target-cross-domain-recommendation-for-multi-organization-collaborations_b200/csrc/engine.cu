@@ -80,6 +80,9 @@ struct dmt_org {
     int dec_blocks;  // grid of the decoder chunk kernel (0: two per SM), dmt_org_set_decoder_blocks
     int gather;      // fused step: 1 = weight / activation rows through bulk-copy rings (bulk.cuh), 0 = plain loads
     int bulk_blocks; // grid of the bulk decoder kernel (0: five per SM)
+    int dec_form;    // register-load decoder of the fused step: 2 = four-warp blocks + next-chunk prefetch, 0 = eight warps
+    int rows_mode;   // fused step, row kernels: 1 = W2 / W3 streamed through shared memory by bulk copies (fused_rows.cu)
+    int rows_R;      // their row tile (fused_rows_per_cta)
     int fanout;  // 1: the backward pass of a step is enqueued as parallel branches (dmt_org_set_fanout)
     float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
     // tables of per-row CSR windows at 128-column tile borders, one per target CSR seen (train targets, predict splits)
@@ -376,12 +379,13 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     if (WANT(K_ENC)) {
         FusedFwd f{br, o->rows_buf, o->d_indptr, o->d_indices, o->d_val, W1t, b1, o->W2t, b2, o->W3t, b3,
                    o->a1, o->a2, o->c, o->a3, drop};
-        if ((rc = launch_fused_fwd(f, B, st))) return rc;
+        if ((rc = o->rows_mode ? launch_fused_fwd_tma(f, B, o->rows_R, st) : launch_fused_fwd(f, B, st))) return rc;
     }
     if (WANT(K_DEC)) {
         FusedDec d{br, o->dec_meta, o->t_batch_chunk, o->pt.batch_cnt, o->t_indices, o->t_val, o->t_inv_perm,
                    o->a3, W4, b4, o->g_sorted, o->dz3, o->loss_rows, o->dz_part, o->loss_part, o->row_cnt};
-        if ((rc = launch_fused_dec(d, o->gather ? o->bulk_blocks : o->dec_blocks, o->gather, st))) return rc;
+        if ((rc = launch_fused_dec(d, o->gather ? o->bulk_blocks : o->dec_blocks, o->gather ? 1 : o->dec_form, st)))
+            return rc;
     }
     // dW4 / db4 only has to be complete before the norm: it runs as a parallel branch of the captured step graph next
     // to the critical path backward rows -> dW3 / dW2 / dW1 (profiling keeps everything on the main stream)
@@ -398,11 +402,12 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     }
     if (WANT(K_SEG_W1)) {
         FusedBwd w{br, o->pt.len, o->dz3, W3, W2, o->a1, o->a2, o->dz2, o->dz1, o->part_db, drop};
-        if ((rc = launch_fused_bwd_rows(w, B, st))) return rc;
+        if ((rc = o->rows_mode ? launch_fused_bwd_rows_tma(w, B, o->rows_R, st) : launch_fused_bwd_rows(w, B, st)))
+            return rc;
     }
     if (WANT(K_DENSE_BWD)) {
         FusedGrad g{br, o->pt.len, o->dz3, o->dz2, o->c, o->a1, o->part_db, G, o->oW2, o->oW3, o->ob1, o->ob2, o->ob3,
-                    o->part_dw, o->dw_cnt};
+                    o->part_dw, o->dw_cnt, o->rows_mode ? o->rows_R : kFusedRows};
         FusedSeg s{o->d_seg_meta, o->pd.batch_chunk_off, o->d_row_sorted, o->d_val_sorted, o->pd.part, o->pd.part_bias,
                    o->d_seg_cnt, o->active, b};
         if ((rc = launch_fused_grad_phase(g, s, o->dz1, G + o->oW1, o->n_enc * 2, st))) return rc;
@@ -688,6 +693,16 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
         o->gather = (env && strcmp(env, "bulk") == 0) ? 1 : 0;  // measured: per-row bulk copies are slower
         env = getenv("DMT_BULK_BLOCKS");
         o->bulk_blocks = env ? atoi(env) : 0;
+        env = getenv("DMT_DEC_FORM");
+        o->dec_form = (env && strcmp(env, "8w") == 0) ? 0 : 2;
+        // Row kernels: weights through shared memory by bulk copies (fused_rows.cu) for small batches, where a row
+        // tile of 2-4 rows and several warps per row pay (Douban shape, 100-row batches: forward rows 130 -> 37 us,
+        // round 240 -> 190 ms); at 500-row batches both forms take 19 / 16 us per launch and the register-streamed
+        // form packs better next to other organizations' kernels (18 organizations: 198 against 224 ms per round).
+        env = getenv("DMT_ROWS");
+        o->rows_R = fused_rows_per_cta(batch_rows);
+        o->rows_mode = o->rows_R < 8 ? 1 : 0;
+        if (env) o->rows_mode = strcmp(env, "tma") == 0 ? 1 : 0;
     }
     A(dalloc(&o->tc_scratch, decoder_tc_scratch_floats(batch_rows, n_dec, H1)));
     A(dalloc(&o->gbuf, t_cap)); A(dalloc(&o->dval_ord, d_cap)); A(dalloc(&o->row_batch, o->rows_cap + 1));
@@ -713,7 +728,8 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
         A(dalloc(&o->t_row_sorted, t_cap)); A(dalloc(&o->d_row_sorted, d_cap)); A(dalloc(&o->t_inv_perm, t_cap));
         A(dalloc(&o->d_val_sorted, d_cap));
         A(dalloc(&o->t_seg_cnt, o->pt.part_rows)); A(dalloc(&o->d_seg_cnt, o->pd.part_rows));
-        A(dalloc(&o->part_db, (int64_t)((batch_rows + kFusedRows - 1) / kFusedRows) * kDbPartStride));
+        A(dalloc(&o->part_db, (int64_t)((batch_rows + 1) / 2 + 1) * kDbPartStride));  // row tiles of >= 2 rows
+        A(prepare_fused_rows());
         A(dalloc(&o->part_dw, (int64_t)16 * 8 * 4096)); A(dalloc(&o->dw_cnt, 16)); A(dalloc(&o->norm_ticket, 1));
         cudaMemsetAsync(o->row_cnt, 0, (size_t)batch_rows * 4, o->st);
         cudaMemsetAsync(o->t_seg_cnt, 0, (size_t)o->pt.part_rows * 4, o->st);
@@ -909,7 +925,8 @@ int dmt_org_predict(dmt_org_t* o, const int32_t* d_indptr, const int32_t* d_indi
         if (o->step_mode == 1 && o->dec_mode == 0) {  // encoder + both dense layers in one row-local launch
             FusedFwd f{br, o->iota_rows, d_indptr, d_indices, d_val, W1t, b1, o->W2t, b2, o->W3t, b3,
                        nullptr, nullptr, nullptr, o->a3, nodrop};
-            if ((rc = launch_fused_fwd(f, m, st))) return rc;
+            if ((rc = o->rows_mode ? launch_fused_fwd_tma(f, m, fused_rows_per_cta(m), st) : launch_fused_fwd(f, m, st)))
+                return rc;
         } else {
             if ((rc = launch_ae_encoder_fwd(o->iota_rows, d_indptr, d_indices, d_val, W1t, b1, H1, o->a1, m, br, st)))
                 return rc;

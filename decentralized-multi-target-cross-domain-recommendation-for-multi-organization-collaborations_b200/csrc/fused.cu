@@ -426,6 +426,160 @@ __device__ __forceinline__ void dec_chunks_bulk_body(const FusedDec& p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 2'' decoder, 4 warps
+// Same contract as dec_chunks_body with the chunk's latency chain shortened: four warps per block share a chunk's
+// targets evenly (up to 32 per warp: eight groups of four rows, so the streaming part of a chunk outweighs its
+// prologue), and the NEXT chunk's metadata, column indices, targets and scatter positions are requested while the
+// current chunk's rows are still in flight (the meta -> index -> row dependency chain of a chunk costs three L2 round
+// trips; two of them now overlap the previous chunk).
+__device__ __forceinline__ void dec_chunks4_body(const FusedDec& p) {
+    constexpr int H = H1c, NW = 4, PER_WARP = kDecChunk / NW, GROUPS = PER_WARP / 4;
+    __shared__ __align__(16) float s_acc[2][NW][H];
+    __shared__ float s_loss[2][NW];
+    __shared__ int s_last;
+    int lo, hi;
+    if (!batch_range(p.br, lo, hi)) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c_lo = p.batch_chunk_off[p.br.b], c_hi = p.batch_chunk_off[p.br.b + 1];
+    int c = c_lo + blockIdx.x;
+    if (c >= c_hi) return;
+    const float inv_n = 1.f / (float)p.n_targets[p.br.b];
+    int4 mt = p.meta[c];
+    int c_l = 0, pos_l = 0;
+    float y_l = 0.f;
+    auto lane_inputs = [&](const int4& m4, int& col, float& y, int& pos) {
+        const int n_tg = m4.w & 0xff;
+        const int per = (n_tg + NW - 1) / NW;
+        const int off = wid * per;
+        const int cnt = max(0, min(per, n_tg - off));
+        col = 0; y = 0.f; pos = 0;
+        if (lane < cnt) {
+            col = p.t_indices[m4.y + off + lane];
+            y = p.target[m4.y + off + lane];
+            pos = p.inv_perm[m4.z + off + lane];
+        }
+    };
+    lane_inputs(mt, c_l, y_l, pos_l);
+    int buf = 0;
+    for (;; buf ^= 1) {
+        const int jl = mt.x;
+        const int n_tg = mt.w & 0xff;               // 1..128 targets in this chunk
+        const int k = (mt.w >> 8) & 0xfff;          // chunk index inside the row
+        const int n_ch = (mt.w >> 20) & 0xfff;      // chunks of the row
+        const int per = (n_tg + NW - 1) / NW;
+        const int cnt = max(0, min(per, n_tg - wid * per));
+        const int cn = c + gridDim.x;
+        const bool more = cn < c_hi;
+        int4 mt_n = mt;
+        if (more) mt_n = p.meta[cn];
+        int c_n = 0, pos_n = 0;
+        float y_n = 0.f;
+        const float* a_row = p.A3 + (int64_t)jl * H;
+        const float4 a0 = ld4(a_row + lane * 4), a1 = ld4(a_row + 128 + lane * 4);
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        float o_l = 0.f;
+        if (cnt > 0) {
+            float4 w[2][4][2];
+            float bb[2][4];
+            auto load_group = [&](int g, int slot) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = __shfl_sync(0xffffffffu, c_l, min(4 * g + q, cnt - 1));
+                    const float* wr = p.W4 + (int64_t)col * H + lane * 4;
+                    w[slot][q][0] = ld4(wr);
+                    w[slot][q][1] = ld4(wr + 128);
+                    bb[slot][q] = p.b4[col];
+                }
+            };
+            load_group(0, 0);
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                if (4 * g < cnt) {
+                    const int slot = g & 1;
+                    if (g + 1 < GROUPS && 4 * (g + 1) < cnt) load_group(g + 1, (g + 1) & 1);
+                    if (g == 0 && more) lane_inputs(mt_n, c_n, y_n, pos_n);  // next chunk's inputs travel with ours
+                    float d[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) d[q] = dot4(a0, w[slot][q][0]) + dot4(a1, w[slot][q][1]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) d[q] = warp_sum(d[q]) + bb[slot][q];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int tq = 4 * g + q;
+                        const bool valid = tq < cnt;
+                        if (lane == tq && valid) o_l = d[q];
+                        const float y = __shfl_sync(0xffffffffu, y_l, min(tq, cnt - 1));
+                        const float gq = valid ? loss_grad(DMT_LOSS_MSE, d[q], y) * inv_n : 0.f;
+                        fma4(acc0, gq, w[slot][q][0]);
+                        fma4(acc1, gq, w[slot][q][1]);
+                    }
+                }
+            }
+        } else if (more) {
+            lane_inputs(mt_n, c_n, y_n, pos_n);
+        }
+        float loss_acc = 0.f;
+        if (lane < cnt) {
+            p.g_sorted[pos_l] = loss_grad(DMT_LOSS_MSE, o_l, y_l) * inv_n;
+            loss_acc = loss_value(DMT_LOSS_MSE, o_l, y_l);
+        }
+        st4(&s_acc[buf][wid][lane * 4], acc0);
+        st4(&s_acc[buf][wid][128 + lane * 4], acc1);
+        loss_acc = warp_sum(loss_acc);
+        if (lane == 0) s_loss[buf][wid] = loss_acc;
+        __syncthreads();
+        const int h = threadIdx.x * 2;  // 128 threads x 2 hidden units
+        float2 s = make_float2(0.f, 0.f);
+        float l = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < NW; ++w4) {
+            const float2 v = *reinterpret_cast<const float2*>(&s_acc[buf][w4][h]);
+            s.x += v.x;
+            s.y += v.y;
+            l += s_loss[buf][w4];
+        }
+        if (n_ch == 1) {
+            const float2 av = *reinterpret_cast<const float2*>(a_row + h);
+            *reinterpret_cast<float2*>(p.dZ3 + (int64_t)jl * H + h) =
+                make_float2(s.x * (1.f - av.x * av.x), s.y * (1.f - av.y * av.y));
+            if (threadIdx.x == 0) p.loss_rows[jl] = l;
+        } else {
+            const int64_t slot = c - c_lo;
+            *reinterpret_cast<float2*>(p.dz_part + slot * H + h) = s;
+            if (threadIdx.x == 0) p.loss_part[slot] = l;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = (atomicAdd(&p.row_cnt[jl], 1) == n_ch - 1);
+            __syncthreads();
+            if (s_last) {  // block-uniform: this chunk arrived last, add the row's partials in chunk order
+                __threadfence();
+                const int64_t first = slot - k;
+                float2 tot = make_float2(0.f, 0.f);
+                for (int q = 0; q < n_ch; ++q) {
+                    const float2 v = __ldcg(reinterpret_cast<const float2*>(p.dz_part + (first + q) * H + h));
+                    tot.x += v.x;
+                    tot.y += v.y;
+                }
+                const float2 av = *reinterpret_cast<const float2*>(a_row + h);
+                *reinterpret_cast<float2*>(p.dZ3 + (int64_t)jl * H + h) =
+                    make_float2(tot.x * (1.f - av.x * av.x), tot.y * (1.f - av.y * av.y));
+                if (threadIdx.x == 0) {
+                    float lt = 0.f;
+                    for (int q = 0; q < n_ch; ++q) lt += __ldcg(p.loss_part + first + q);
+                    p.loss_rows[jl] = lt;
+                    p.row_cnt[jl] = 0;
+                }
+            }
+        }
+        if (!more) break;
+        c = cn;
+        mt = mt_n;
+        c_l = c_n;
+        y_l = y_n;
+        pos_l = pos_n;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ 3a backward rows
 template <int R>
 __device__ __forceinline__ void bwd_rows_body(const FusedBwd& p, int cta) {
@@ -732,7 +886,7 @@ __device__ __forceinline__ void dw_tile_body(const FusedGrad& p, int role) {
 __device__ __forceinline__ void db_finish_body(const FusedGrad& p) {
     int lo, hi;
     if (!batch_range(p.br, lo, hi)) return;
-    const int n_cta = (hi - lo + kFusedRows - 1) / kFusedRows;
+    const int n_cta = (hi - lo + p.rows_per_cta - 1) / p.rows_per_cta;
     const int t = threadIdx.x;
     float s3 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int q = 0; q < n_cta; ++q) {
@@ -750,6 +904,8 @@ __device__ __forceinline__ void db_finish_body(const FusedGrad& p) {
 __global__ void __launch_bounds__(256) ae_fwd_rows_kernel(FusedFwd p) { fwd_rows_body<kFusedRows>(p, blockIdx.x); }
 
 __global__ void __launch_bounds__(256) ae_dec_chunks_kernel(FusedDec p) { dec_chunks_body(p); }
+
+__global__ void __launch_bounds__(128, 4) ae_dec_chunks4_kernel(FusedDec p) { dec_chunks4_body(p); }
 
 __global__ void __launch_bounds__(kBulkWarps * 32) ae_dec_chunks_bulk_kernel(FusedDec p) { dec_chunks_bulk_body(p); }
 
@@ -969,6 +1125,12 @@ int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_
     if (gather == 1) {  // bulk-copy rings: five 128-thread blocks per SM
         const int blocks = blocks_hint > 0 ? blocks_hint : kNumSMs * 5;
         ae_dec_chunks_bulk_kernel<<<blocks, kBulkWarps * 32, 0, st>>>(p);
+        DMT_LAUNCH_CHECK();
+        return 0;
+    }
+    if (gather == 2) {  // four-warp blocks with next-chunk prefetch; blocks_hint counts 256-thread blocks
+        const int blocks = blocks_hint > 0 ? blocks_hint * 2 : kNumSMs * 4;
+        ae_dec_chunks4_kernel<<<blocks, 128, 0, st>>>(p);
         DMT_LAUNCH_CHECK();
         return 0;
     }

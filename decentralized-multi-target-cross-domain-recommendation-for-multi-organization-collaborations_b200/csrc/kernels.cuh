@@ -205,6 +205,7 @@ struct FusedGrad {
     int64_t oW2, oW3, ob1, ob2, ob3;
     float* part_dw;                  // [16 tiles x 8 slices x 64 x 64]
     int* dw_cnt;                     // [16]
+    int rows_per_cta;                // row tile of the backward-rows kernel that wrote part_db
 };
 struct FusedPlanSide {
     int64_t n_entries;
@@ -226,6 +227,11 @@ struct FusedPlanArgs {
 int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st);
 // gather: 0 = rows through registers (plain loads), 1 = rows through shared-memory rings (bulk copies, bulk.cuh)
 int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st);
+// fused_rows.cu: the row kernels with W2 / W3 streamed through shared memory by 32 KB bulk copies; R = rows per CTA
+int fused_rows_per_cta(int batch_rows);
+int prepare_fused_rows();
+int launch_fused_fwd_tma(const FusedFwd& p, int n_rows_max, int R, cudaStream_t st);
+int launch_fused_bwd_rows_tma(const FusedBwd& p, int n_rows_max, int R, cudaStream_t st);
 int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st);
 int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, float* bias_grad, int n_chunk_max,
                             int gather, cudaStream_t st);

@@ -9,6 +9,8 @@ reused across calls, keyed by the content of the CSR structure.
 import sys
 import weakref
 
+import os
+
 import numpy as np
 import torch
 from scipy.sparse import csr_matrix
@@ -77,7 +79,9 @@ def _rng_mode():
     """'reference': consume torch's CPU generator exactly like the reference (data-loader seeds, parameter init,
     dropout masks drawn on the host) so a run replays bit-for-bit comparable batches; 'device' (default): same
     parameter init and sampler, dropout drawn by the on-device counter-based generator."""
-    return cfg['dmt_rng'] if 'dmt_rng' in cfg else 'device'
+    if 'dmt_rng' in cfg:
+        return cfg['dmt_rng']
+    return os.environ.get('DMT_RNG', 'device')  # an unmodified driver cannot add cfg keys: the environment can
 
 
 def _shape_target():

@@ -52,6 +52,12 @@ def main():
     sys.path[:0] = [dmtcdr_b200.DROPIN_DIR, src]
     os.chdir(src)
     sys.argv = [driver] + args
+    import assist as _a, models as _m, organization as _o  # noqa: E401  (what the driver's own imports will resolve to)
+
+    here = os.path.abspath(dmtcdr_b200.DROPIN_DIR)
+    if not all(os.path.abspath(x.__file__).startswith(here) for x in (_a, _m, _o)):
+        raise SystemExit("launch_reference: models / assist / organization did not resolve to the drop-in")
+    print("dmtcdr_b200 drop-in active: models, assist, organization <- {}".format(here), flush=True)
     runpy.run_path(driver, run_name="__main__")
 
 

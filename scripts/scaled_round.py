@@ -1,42 +1,73 @@
-"""Scaled-shape sanity/roofline run (config-5 family, reduced to fit a short GPU call):
-   100 000 users x 50 000 items, ~20 M ratings, 8 random organizations, batch 500 rows, 1 local epoch per round.
-   Prints one JSON object with the round time, the per-kernel-class step times of organization 0 and the
-   HBM fractions of the streaming kernels. Not part of the bench contract (bench.py is the ML1M headline)."""
+"""Scaled-shape run of the config-5 family (BASELINE.json configs[4]: 1M users x 500K items, 1B ratings, 64
+organizations over 8 GPUs), reduced so that one GPU call of a few minutes covers it:
+
+    python scripts/scaled_round.py [M N NNZ K WORLD EPOCHS]      defaults: 400000 200000 100000000 64 8 1
+
+builds M x N synthetic ratings (Zipf item popularity), splits the items into K random organizations
+(`random-K`, src/data.py:231-235) and runs assistance rounds for RANK 0 of a WORLD-rank org-sharded job on this GPU:
+its K / WORLD organizations train (EPOCHS local epochs, batches of 500 users, per-epoch plans) and predict, then the
+combine runs over all K rows of the prediction matrix exactly as on every rank of the real job (the other ranks' rows
+stay zero: same bytes, same kernels; only the NCCL all-gather itself is not exercised here - bench.py --gpus N does
+that at ML1M shape). Prints one JSON object: round time, rating-visits/s of this rank, the per-kernel-class step times
+of one organization with their algorithmic bytes against the measured HBM peak, and the round's aggregate rate.
+Not part of the bench contract (bench.py is the ML1M headline)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
-import dmtcdr_b200
-from dmtcdr_b200 import roundloop, synth, native
+import dmtcdr_b200  # noqa: F401
+from dmtcdr_b200 import engine as E
+from dmtcdr_b200 import roundloop, synth
 
-M, N, NNZ, K = 100_000, 50_000, 20_000_000, 8
+a = [int(x) for x in sys.argv[1:]]
+M, N, NNZ, K, WORLD, EPOCHS = (a + [400_000, 200_000, 100_000_000, 64, 8, 1][len(a):])[:6]
+BS = 500
 t0 = time.time()
-data = synth.make_scaled_data(M, N, NNZ, 8, seed=0)
+data = synth.make_scaled_data_device(M, N, NNZ, 8, seed=0)
 gen_s = time.time() - t0
 torch.manual_seed(0)
 chunks = list(torch.randperm(N).split(N // K))
 split = [c.numpy() for c in chunks[:K - 1]] + [torch.cat(chunks[K - 1:]).numpy()]
 mats = {"train": (data.train, data.train), "test": (data.train, data.test)}
-R = roundloop.AssistRounds(mats, split, "explicit", 500, local_epochs=1, device="cuda:0")
+t0 = time.time()
+R = roundloop.AssistRounds(mats, split, "explicit", BS, local_epochs=EPOCHS, device="cuda:0", rank=0, world=WORLD,
+                           whole_round=False)
 R.round0()
-R.run_round(1); R.sync()
+setup_s = time.time() - t0
+R.run_round(1)
+R.sync()
 ts = []
 for t in (2, 3):
-    torch.cuda.synchronize(); a = time.perf_counter()
-    R.run_round(t); R.sync()
-    ts.append(time.perf_counter() - a)
-eng = R.eng[0]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    R.run_round(t)
+    e1.record()
+    R.sync()
+    ts.append(e0.elapsed_time(e1) * 1e-3)
+sec = min(ts)
+org = R.my_orgs[0]
+eng = R.eng[org]
 prof = eng.h.profile_step(b=0, reps=10)
 hbm, src = bench.measured_peaks()
 n_params = eng.h.n_params
-t_batch = float(np.mean([eng.t_len[r:r + 500].sum() for r in range(0, 5000, 500)]))
-visits = K * (1 * data.train.nnz + data.train.nnz + data.test.nnz)
-out = {"shape": [M, N, int(data.train.nnz), int(data.test.nnz)], "orgs": K, "gen_seconds": gen_s,
-       "round_ms": 1e3 * min(ts), "rating_visits_per_s": visits / min(ts), "step_kernel_ms": prof,
-       "n_params_per_org": int(n_params),
-       "adam": {"bytes": n_params * 32, "GBps": n_params * 32 / (prof["clip_adam"] * 1e-3) / 1e9,
-                "frac_of_hbm_peak": n_params * 32 / (prof["clip_adam"] * 1e-3) / 1e9 / hbm},
-       "decoder": {"targets_per_batch": t_batch, "bytes": t_batch * (4 * 256 + 20),
-                   "GBps": t_batch * (4 * 256 + 20) / (prof["decoder_loss_dz3"] * 1e-3) / 1e9},
-       "grad_norm": {"GBps": n_params * 4 / (prof["grad_norm"] * 1e-3) / 1e9}, "hbm_peak": hbm}
+n_tr, n_te = data.train.nnz, data.test.nnz
+nb = -(-M // BS)
+t_batch, d_batch = n_tr / nb, float(eng.d_len.sum()) / nb
+by_class = bench.step_algorithmic_bytes(t_batch, d_batch, min(N, int(t_batch)), min(eng.n_enc, int(d_batch)), BS, n_params)
+classes = {k: {"ms": v, "algorithmic_bytes": by_class[k], "GBps": by_class[k] / (v * 1e-3) / 1e9,
+               "frac_of_hbm_peak": by_class[k] / (v * 1e-3) / 1e9 / hbm} for k, v in prof.items() if k in by_class}
+n_local = len(R.my_orgs)
+visits_rank = n_local * (EPOCHS * n_tr + n_tr + n_te)
+agg = E.bytes_per_round(n_local, n_tr, n_te, M, [len(split[k]) for k in R.my_orgs], N, EPOCHS, BS)
+agg += (n_tr + n_te) * (4 * K + 24) - (n_tr + n_te) * (4 * n_local + 24)  # the combine reads all K rows
+out = {"shape": {"users": M, "items": N, "train": int(n_tr), "test": int(n_te)}, "organizations": K, "world": WORLD,
+       "organizations_on_this_rank": n_local, "local_epochs": EPOCHS, "batch_rows": BS,
+       "host_seconds": {"generate": gen_s, "setup_and_round0": setup_s},
+       "round_ms": 1e3 * sec, "rating_visits_per_s_this_rank": visits_rank / sec,
+       "rating_visits_per_s_job_if_all_ranks_match": K * (EPOCHS * n_tr + n_tr + n_te) / sec,
+       "n_params_per_org": int(n_params), "step_classes": classes, "step_sum_us": 1e3 * sum(prof.values()),
+       "round_aggregate": {"algorithmic_bytes": agg, "GBps": agg / sec / 1e9, "frac_of_hbm_peak": agg / sec / 1e9 / hbm},
+       "hbm_peak_GBps": hbm, "peak_source": src,
+       "device_memory_used_GB": (torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9}
 print(json.dumps(out))

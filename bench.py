@@ -71,6 +71,7 @@ def ncu_per_kernel(path=NCU_RAW):
     {kernel: {'dram_bytes', 'l2_to_sm_bytes', 'us', 'regs', 'launches'}}. Raises when the file is missing: the
     roofline block's `traffic` is measured evidence or nothing."""
     import csv
+    import re
 
     if not os.path.exists(path):
         raise FileNotFoundError("{} is missing: run scripts/r2_prof.sh under gpurun and commit its raw page".format(path))
@@ -87,7 +88,8 @@ def ncu_per_kernel(path=NCU_RAW):
     for r in rows[2:]:
         if len(r) != len(hdr):
             continue
-        name = r[col["Kernel Name"]].split("(")[0].split("::")[-1]
+        ids = re.findall(r"([A-Za-z_]\w*)(?=[<(])", r[col["Kernel Name"]])
+        name = next((x for x in ids if x.endswith("_kernel")), ids[0] if ids else r[col["Kernel Name"]])
         a = acc.setdefault(name, {"dram_bytes": 0.0, "l2_to_sm_bytes": 0.0, "us": 0.0, "regs": 0, "launches": 0})
         a["dram_bytes"] += val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
         a["l2_to_sm_bytes"] += val(r, "l1tex__m_xbar2l1tex_read_bytes.sum")
@@ -101,7 +103,7 @@ def ncu_per_kernel(path=NCU_RAW):
 
 
 # profile_step class -> kernel of csrc/fused.cu (bulk gather mode / register-load mode)
-CLASS_KERNEL = {"fwd_rows": ("ae_fwd_rows_kernel",) * 2, "decoder_loss_dz3": ("ae_dec_chunks_bulk_kernel", "ae_dec_chunks_kernel"),
+CLASS_KERNEL = {"fwd_rows": ("ae_fwd_rows_kernel",) * 2, "decoder_loss_dz3": ("ae_dec_chunks_bulk_kernel", "ae_dec_chunks4_kernel"),
                 "dw4_segments": ("ae_seg_chunks_bulk_kernel", "ae_seg_chunks_kernel"), "bwd_rows": ("ae_bwd_rows_kernel",) * 2,
                 "grad_phase": ("ae_grad_phase_kernel",) * 2, "grad_norm": ("norm_prepare_kernel",) * 2,
                 "clip_adam": ("adam_shadow_kernel",) * 2}

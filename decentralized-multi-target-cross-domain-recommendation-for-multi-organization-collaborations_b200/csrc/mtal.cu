@@ -240,6 +240,167 @@ __global__ void assist_rows_w_finish_kernel(const float* __restrict__ scratch, c
     }
 }
 
+// ---------------------------------------------------------------- L-BFGS on the device
+// torch.optim.LBFGS(lr, max_iter = 20, max_eval = 25, tolerance_grad = 1e-7, tolerance_change = 1e-9,
+// history_size = 100, no line search) as the reference runs it on models.assist (src/utils.py:255-256,
+// src/assist.py:118-129), restated as ONE single-block kernel per inner iteration so that a whole fit is a chain of
+// launches with no host round trip: the host enqueues, per optimizer.step(): closure, begin (it = 0), then for
+// it = 1..max_iter: {check of iteration it-1 + direction / step of iteration it} and, while it < max_iter, the
+// closure at the moved point, which skips itself (need_eval) once this step() call has met a stopping rule.
+// Vectors live in global memory; reductions are block sums (one warp when P <= 32, e.g. the K assistance weights).
+constexpr int kLbfgsStateFloats = 16;
+struct LbfgsState {
+    float loss, prev_loss, t, H_diag;
+    int n_iter;     // state['n_iter'] of torch: counts over all step() calls
+    int num_old, head;
+    int step_done;  // this step() call has returned / broken out of its loop
+    int need_eval;  // the closure after this kernel has to run (read by the closure kernels)
+    int cur_evals;
+    int pad[6];
+};
+static_assert(sizeof(LbfgsState) == kLbfgsStateFloats * sizeof(float), "state size");
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    float r = (lane < nw) ? sh[lane] : 0.f;  // all operands are magnitudes (>= 0)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    return r;
+}
+
+__global__ void lbfgs_step_kernel(LbfgsState* __restrict__ st, const float* __restrict__ loss_new,
+                                  float* __restrict__ x, const float* __restrict__ g, float* __restrict__ d,
+                                  float* __restrict__ prev_g, float* __restrict__ q, float* __restrict__ ty,
+                                  float* __restrict__ ts, float* __restrict__ Y, float* __restrict__ S,
+                                  float* __restrict__ ro, float* __restrict__ al, int P, int it, int max_iter, float lr,
+                                  int hist) {
+    __shared__ float sh[32];
+    const float tol_grad = 1e-7f, tol_change = 1e-9f;
+    const int max_eval = max_iter * 5 / 4;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    LbfgsState s = *st;  // every thread holds the same copy; thread 0 writes it back
+    __syncthreads();
+    auto dot = [&](const float* a, const float* b) {
+        float v = 0.f;
+        for (int i = tid; i < P; i += nt) v += a[i] * b[i];
+        return block_sum(v, sh);
+    };
+    auto absmax = [&](const float* a, float scale) {
+        float v = 0.f;
+        for (int i = tid; i < P; i += nt) v = fmaxf(v, fabsf(a[i] * scale));
+        return block_max(v, sh);
+    };
+    auto finish = [&]() {
+        if (tid == 0) *st = s;
+    };
+    if (it == 0) {  // after the first closure of a step() call
+        s.loss = *loss_new;
+        s.cur_evals = 1;
+        s.need_eval = 0;
+        s.step_done = absmax(g, 1.f) <= tol_grad ? 1 : 0;
+        finish();
+        return;
+    }
+    if (s.step_done) {
+        s.need_eval = 0;
+        finish();
+        return;
+    }
+    if (s.need_eval) {  // iteration it-1 re-evaluated the closure: its stopping rules, in torch's order
+        s.loss = *loss_new;
+        s.cur_evals += 1;
+        const bool opt_cond = absmax(g, 1.f) <= tol_grad;
+        const float step_max = absmax(d, s.t);
+        if (s.cur_evals >= max_eval || opt_cond || step_max <= tol_change || fabsf(s.loss - s.prev_loss) < tol_change) {
+            s.step_done = 1;
+            s.need_eval = 0;
+            finish();
+            return;
+        }
+    }
+    // ---- iteration `it`: direction
+    s.n_iter += 1;
+    if (s.n_iter == 1) {
+        for (int i = tid; i < P; i += nt) d[i] = -g[i];
+        s.num_old = 0;
+        s.head = 0;
+        s.H_diag = 1.f;
+    } else {
+        for (int i = tid; i < P; i += nt) {
+            ty[i] = g[i] - prev_g[i];
+            ts[i] = d[i] * s.t;
+        }
+        __syncthreads();
+        const float ys = dot(ty, ts);
+        if (ys > 1e-10f) {
+            if (s.num_old == hist) {  // old_dirs.pop(0)
+                s.head = (s.head + 1) % hist;
+                s.num_old -= 1;
+            }
+            const int slot = (s.head + s.num_old) % hist;
+            for (int i = tid; i < P; i += nt) {
+                Y[(int64_t)slot * P + i] = ty[i];
+                S[(int64_t)slot * P + i] = ts[i];
+            }
+            if (tid == 0) ro[slot] = 1.f / ys;
+            s.num_old += 1;
+            __syncthreads();
+            s.H_diag = ys / dot(ty, ty);
+        }
+        for (int i = tid; i < P; i += nt) q[i] = -g[i];
+        __syncthreads();
+        for (int j = s.num_old - 1; j >= 0; --j) {
+            const int slot = (s.head + j) % hist;
+            const float a = dot(S + (int64_t)slot * P, q) * ro[slot];
+            if (tid == 0) al[slot] = a;
+            for (int i = tid; i < P; i += nt) q[i] -= a * Y[(int64_t)slot * P + i];
+            __syncthreads();
+        }
+        for (int i = tid; i < P; i += nt) d[i] = q[i] * s.H_diag;
+        __syncthreads();
+        for (int j = 0; j < s.num_old; ++j) {
+            const int slot = (s.head + j) % hist;
+            const float be = dot(Y + (int64_t)slot * P, d) * ro[slot];
+            const float c = al[slot] - be;
+            for (int i = tid; i < P; i += nt) d[i] += c * S[(int64_t)slot * P + i];
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < P; i += nt) prev_g[i] = g[i];
+    s.prev_loss = s.loss;
+    // ---- step length
+    if (s.n_iter == 1) {
+        float v = 0.f;
+        for (int i = tid; i < P; i += nt) v += fabsf(g[i]);
+        v = block_sum(v, sh);
+        s.t = fminf(1.f, 1.f / v) * lr;
+    } else {
+        s.t = lr;
+    }
+    const float gtd = dot(g, d);
+    if (gtd > -tol_change) {  // directional derivative below tolerance: break before moving
+        s.step_done = 1;
+        s.need_eval = 0;
+        finish();
+        return;
+    }
+    for (int i = tid; i < P; i += nt) x[i] += s.t * d[i];
+    if (it != max_iter) {
+        s.need_eval = 1;
+    } else {
+        s.need_eval = 0;
+        s.step_done = 1;
+    }
+    finish();
+}
+
 // ---------------------------------------------------------------- fused loss + grad of models.Assist
 // scratch layout: [0] loss partials (NB), then d_s partials (NB x K). One warp per owned column (segment) so the
 // per-column rate gradient is a warp-segmented reduction without atomics; the K-vector d_s is reduced per block
@@ -253,10 +414,12 @@ __global__ void __launch_bounds__(256) assist_loss_grad_kernel(const float* __re
                                                                const float* __restrict__ rate,
                                                                const float* __restrict__ w, int64_t n, int n_rate, int K,
                                                                int kind, float* __restrict__ d_rate,
-                                                               float* __restrict__ scratch) {
+                                                               float* __restrict__ scratch,
+                                                               const int* __restrict__ run_flag) {
     __shared__ float s_soft[kAssistKMax];
     __shared__ float s_ds[8][kAssistKMax];
     __shared__ float s_loss[8];
+    if (run_flag != nullptr && *run_flag == 0) return;  // device-side L-BFGS: this evaluation is not needed
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         float mx = -INFINITY;
@@ -315,10 +478,12 @@ __global__ void __launch_bounds__(256) assist_loss_grad_kernel(const float* __re
 }
 
 __global__ void assist_finish_kernel(const float* __restrict__ scratch, const float* __restrict__ w, int K, int nb,
-                                     float* __restrict__ out_loss, float* __restrict__ d_w) {
+                                     float* __restrict__ out_loss, float* __restrict__ d_w,
+                                     const int* __restrict__ run_flag) {
     __shared__ float sh[32];
     __shared__ float s_soft[kAssistKMax];
     __shared__ float s_ds[kAssistKMax];
+    if (run_flag != nullptr && *run_flag == 0) return;
     float l = 0.f;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) l += scratch[i];
     l = block_sum(l, sh);
@@ -502,10 +667,64 @@ int dmt_assist_loss_grad(const float* h, const float* t, const float* V, const i
     int nb = (n_rate + 7) / 8;
     if (nb > kAssistBlocks) nb = kAssistBlocks;
     assist_loss_grad_kernel<<<nb, 256, 0, as_stream(stream)>>>(h, t, V, seg_off, rate, w, n, n_rate, K, loss_kind,
-                                                              d_rate, scratch);
+                                                              d_rate, scratch, nullptr);
     DMT_LAUNCH_CHECK();
-    assist_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(scratch, w, K, nb, out_loss, d_w);
+    assist_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(scratch, w, K, nb, out_loss, d_w, nullptr);
     DMT_LAUNCH_CHECK();
+    return 0;
+}
+
+// Workspace of one device-side fit (floats): state | loss_new | grads[n_rate + K] | d, prev_g, q, ty, ts [5 x P] |
+// ro, al [2 x H] | old_dirs, old_stps [2 x H x P], with P = n_rate + K (the upper bound of the optimised slice).
+int64_t dmt_assist_fit_work_floats(int n_rate, int K, int history) {
+    const int64_t Pm = (int64_t)n_rate + K;
+    return kLbfgsStateFloats + 1 + Pm + 5 * Pm + 2 * (int64_t)history + 2 * (int64_t)history * Pm;
+}
+
+int dmt_assist_fit(const float* h, const float* t, const float* V, const int32_t* seg_off, int64_t n, int n_rate, int K,
+                   int loss_kind, float* params, int ar_optim, int aw_optim, float lr, int steps, int max_iter,
+                   int history, float* work, float* scratch, void* stream) {
+    DMT_REQUIRE(n > 0 && n_rate > 0 && K >= 1 && K <= kAssistKMax && params && work && scratch,
+                "dmt_assist_fit: need n>0 and 1 <= K <= 64");
+    DMT_REQUIRE((ar_optim || aw_optim) && steps > 0 && max_iter > 0 && history > 0, "dmt_assist_fit: nothing to fit");
+    cudaStream_t st = as_stream(stream);
+    const int64_t Pm = (int64_t)n_rate + K;
+    const int off = ar_optim ? 0 : n_rate;
+    const int P = (ar_optim ? n_rate : 0) + (aw_optim ? K : 0);
+    LbfgsState* state = reinterpret_cast<LbfgsState*>(work);
+    float* loss_new = work + kLbfgsStateFloats;
+    float* grads = loss_new + 1;
+    float* vec = grads + Pm;  // d | prev_g | q | ty | ts
+    float* ro = vec + 5 * Pm;
+    float* al = ro + history;
+    float* Y = al + history;
+    float* S = Y + (int64_t)history * Pm;
+    DMT_CUDA(cudaMemsetAsync(work, 0, sizeof(float) * (kLbfgsStateFloats + 1), st));
+    int nb = (n_rate + 7) / 8;
+    if (nb > kAssistBlocks) nb = kAssistBlocks;
+    const int threads = P <= 32 ? 32 : 256;
+    const float* rate = params;
+    const float* w = params + n_rate;
+    auto eval = [&](const int* flag) -> int {
+        assist_loss_grad_kernel<<<nb, 256, 0, st>>>(h, t, V, seg_off, rate, w, n, n_rate, K, loss_kind, grads, scratch,
+                                                    flag);
+        DMT_LAUNCH_CHECK();
+        assist_finish_kernel<<<1, 256, 0, st>>>(scratch, w, K, nb, loss_new, grads + n_rate, flag);
+        DMT_LAUNCH_CHECK();
+        return 0;
+    };
+    int rc;
+    for (int s_ = 0; s_ < steps; ++s_) {  // optimizer.step(closure) x cfg['assist']['num_epochs'] (src/assist.py:118-129)
+        if ((rc = eval(nullptr))) return rc;
+        for (int it = 0; it <= max_iter; ++it) {
+            lbfgs_step_kernel<<<1, threads, 0, st>>>(state, loss_new, params + off, grads + off, vec, vec + Pm,
+                                                     vec + 2 * Pm, vec + 3 * Pm, vec + 4 * Pm, Y, S, ro, al, P, it,
+                                                     max_iter, lr, history);
+            DMT_LAUNCH_CHECK();
+            if (it >= 1 && it < max_iter)
+                if ((rc = eval(&state->need_eval))) return rc;
+        }
+    }
     return 0;
 }
 

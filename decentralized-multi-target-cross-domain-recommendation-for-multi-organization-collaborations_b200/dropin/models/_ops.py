@@ -17,6 +17,29 @@ def _need_cuda(*ts):
                                      "move the model and the batch to cfg['device']='cuda'")
 
 
+_SORT_CACHE = {}
+
+
+def sorted_segments(idx, bound):
+    """native.sort_segments memoised on the index tensor: the NCF head and the tower input of one step gather with the
+    same user / item vectors, so each is sorted once per step instead of once per autograd node (the cache holds the
+    tensors of the latest step only)."""
+    key = (idx.data_ptr(), idx.numel(), int(bound), idx._version)
+    hit = _SORT_CACHE.get(key)
+    if hit is not None and hit[0] is idx:
+        return hit[1]
+    if len(_SORT_CACHE) >= 8:
+        _SORT_CACHE.clear()
+    seg = native.sort_segments(idx, bound)
+    _SORT_CACHE[key] = (idx, seg)
+    return seg
+
+
+def _scaled(t, dloss, n):
+    """t * dloss / n without reading dloss on the host (float(dloss) would drain the stream every step)."""
+    return None if t is None else t * (dloss / n)
+
+
 def batch_csr(row_ids, cols, vals, rows_sorted):
     """Batch-local CSR of COO triples: local row = rank of row_ids in rows_sorted; stable within a row."""
     r = torch.searchsorted(rows_sorted, row_ids)
@@ -148,15 +171,15 @@ class MFFn(torch.autograd.Function):
             return (None,) * 11
         user, item, Wu, Wi, bu, bi, pu, pi, dpred, sums = ctx.saved_tensors
         n = user.numel()
-        scale = float(dloss) / n
-        seg_u = native.sort_segments(user, Wu.shape[0])
-        seg_i = native.sort_segments(item, Wi.shape[0])
-        dWu, dbu = native.mf_bwd_table(item, Wi, bi, pu, dpred, scale, seg_u, Wu.shape[0])
-        dWi, dbi = native.mf_bwd_table(user, Wu, bu, pi, dpred, scale, seg_i, Wi.shape[0])
-        dbias = (sums[1] * scale).reshape(1)
-        dpu = native.mf_bwd_side(user, Wu, bu, dpred, scale) if pu is not None else None
-        dpi = native.mf_bwd_side(item, Wi, bi, dpred, scale) if pi is not None else None
-        return None, None, None, dWu, dWi, dbu.view(-1, 1), dbi.view(-1, 1), dbias, dpu, dpi, None
+        seg_u = sorted_segments(user, Wu.shape[0])
+        seg_i = sorted_segments(item, Wi.shape[0])
+        dWu, dbu = native.mf_bwd_table(item, Wi, bi, pu, dpred, 1.0, seg_u, Wu.shape[0])
+        dWi, dbi = native.mf_bwd_table(user, Wu, bu, pi, dpred, 1.0, seg_i, Wi.shape[0])
+        dpu = native.mf_bwd_side(user, Wu, bu, dpred, 1.0) if pu is not None else None
+        dpi = native.mf_bwd_side(item, Wi, bi, dpred, 1.0) if pi is not None else None
+        sc = lambda t: _scaled(t, dloss, n)  # noqa: E731
+        return (None, None, None, sc(dWu), sc(dWi), sc(dbu).view(-1, 1), sc(dbi).view(-1, 1), sc(sums[1]).reshape(1),
+                sc(dpu), sc(dpi), None)
 
 
 class EmbedCatFn(torch.autograd.Function):
@@ -179,8 +202,8 @@ class EmbedCatFn(torch.autograd.Function):
         user, item = ctx.saved_tensors
         nu, ni, H = ctx.sizes
         dOut = dOut.contiguous()
-        dWu, dbu = native.embed_bwd(dOut, 0, H, native.sort_segments(user, nu), nu)
-        dWi, dbi = native.embed_bwd(dOut, H, H, native.sort_segments(item, ni), ni)
+        dWu, dbu = native.embed_bwd(dOut, 0, H, sorted_segments(user, nu), nu)
+        dWi, dbi = native.embed_bwd(dOut, H, H, sorted_segments(item, ni), ni)
         return None, None, dWu, dbu.view(-1, 1), dWi, dbi.view(-1, 1)
 
 
@@ -213,15 +236,16 @@ class GMFLossFn(torch.autograd.Function):
             return (None,) * 12
         user, item, Wu, Wi, bu, bi, pu, pi, cs, dpred, q = ctx.saved_tensors
         n = user.numel()
-        scale = float(dloss) / n
-        seg_u = native.sort_segments(user, Wu.shape[0])
-        seg_i = native.sort_segments(item, Wi.shape[0])
-        dWu, dbu = native.mf_bwd_table(item, Wi, bi, pu, dpred, scale, seg_u, Wu.shape[0], cs)
-        dWi, dbi = native.mf_bwd_table(user, Wu, bu, pi, dpred, scale, seg_i, Wi.shape[0], cs)
-        dpu = native.mf_bwd_side(user, Wu, bu, dpred, scale, cs) if pu is not None else None
-        dpi = native.mf_bwd_side(item, Wi, bi, dpred, scale, cs) if pi is not None else None
-        dcs = native.weighted_colsum(dpred, q, scale)
-        return (None, None, None, dWu, dWi, dbu.view(-1, 1), dbi.view(-1, 1), dpu, dpi, dcs, dpred * scale, None)
+        seg_u = sorted_segments(user, Wu.shape[0])
+        seg_i = sorted_segments(item, Wi.shape[0])
+        dWu, dbu = native.mf_bwd_table(item, Wi, bi, pu, dpred, 1.0, seg_u, Wu.shape[0], cs)
+        dWi, dbi = native.mf_bwd_table(user, Wu, bu, pi, dpred, 1.0, seg_i, Wi.shape[0], cs)
+        dpu = native.mf_bwd_side(user, Wu, bu, dpred, 1.0, cs) if pu is not None else None
+        dpi = native.mf_bwd_side(item, Wi, bi, dpred, 1.0, cs) if pi is not None else None
+        dcs = native.weighted_colsum(dpred, q, 1.0)
+        sc = lambda t: _scaled(t, dloss, n)  # noqa: E731
+        return (None, None, None, sc(dWu), sc(dWi), sc(dbu).view(-1, 1), sc(dbi).view(-1, 1), sc(dpu), sc(dpi), sc(dcs),
+                sc(dpred), None)
 
 
 class LossFn(torch.autograd.Function):

@@ -480,12 +480,57 @@ class MtalState:
             opt.step(closure)
         return rate.detach(), weight.detach()
 
+    def fit_owners_device(self, F_prev, ar, ar_mode, aw_mode, match_rate, lr=0.1, steps=10):
+        """All owners' L-BFGS fits (src/assist.py:118-129) with the optimizer itself on the device
+        (dmt_assist_fit: closure, two-loop recursion, step and torch's stopping rules as a chain of launches, no host
+        round trip), the owners spread over a few side streams; ONE device->host copy of all fitted rates / weights at
+        the end. (The host-driven variant, fit_owner, pays one synchronous read-back per closure evaluation and
+        torch.optim.LBFGS's per-iteration Python walk over up to 100 history pairs: ~110 ms per Amazon-shape round.)"""
+        main = torch.cuda.current_stream()
+        n_side = min(self.K, 4)
+        if getattr(self, "_fit_streams", None) is None or len(self._fit_streams) < n_side:
+            self._fit_streams = [torch.cuda.Stream(device=self.device) for _ in range(n_side)]
+        sizes = [self.split_sizes[i] + self.K for i in range(self.K)]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        init = np.empty(int(offs[-1]), np.float32)
+        for i in range(self.K):
+            init[offs[i]:offs[i] + self.split_sizes[i]] = float(ar)
+            init[offs[i] + self.split_sizes[i]:offs[i + 1]] = 1.0 / self.K
+        params = to_dev(init, self.device)
+        ready = main.record_event()
+        keep = []
+        for i in range(self.K):
+            v = self.owner_view("train", i)
+            n = v["n"]
+            n_match = int(n * match_rate) if match_rate < 1 else n
+            side = self._fit_streams[i % n_side]
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                h, t, V = native.assist_gather_view(F_prev, self.y["train"].data, self.O_full["train"], v["pos"],
+                                                    v["rank"], i, n_match, org_row=self.org_row, K=self.K)
+                keep.append((h, t, V) + native.assist_fit(h, t, V, v["seg_off"], params[offs[i]:offs[i + 1]],
+                                                          ar_mode == "optim", aw_mode == "optim", self.loss_kind,
+                                                          lr=lr, steps=steps))
+        for side in self._fit_streams[:n_side]:
+            main.wait_stream(side)
+        host = to_host(params)  # synchronises the main stream: every buffer in `keep` has been consumed
+        del keep
+        fitted = []
+        for i in range(self.K):
+            r = host[offs[i]:offs[i] + self.split_sizes[i]].clone()
+            w = host[offs[i] + self.split_sizes[i]:offs[i + 1]].clone()
+            fitted.append((r, w))
+        return fitted
+
     def update(self, F_prev: dict, ar, ar_mode="constant", aw_mode="constant", match_rate=1.0, out=None, cold=False):
         """Assist.update (src/assist.py:81-179): fit per owner on train, then ONE combine pass per split.
         cold: cold-start run — organization 0's output is NaN on the aligned rows it never saw; those entries combine
         organizations 1.. with softmax(w[1:]) (src/models/assist.py:28-34)."""
-        fitted = [self.fit_owner(i, F_prev["train"], ar, ar_mode, aw_mode, match_rate, cold=cold)
-                  for i in range(self.K)]
+        if (ar_mode == "optim" or aw_mode == "optim") and not cold and os.environ.get("DMT_LBFGS", "device") != "host":
+            fitted = self.fit_owners_device(F_prev["train"], ar, ar_mode, aw_mode, match_rate)
+        else:
+            fitted = [self.fit_owner(i, F_prev["train"], ar, ar_mode, aw_mode, match_rate, cold=cold)
+                      for i in range(self.K)]
         rate_col = np.zeros(self.n_cols, np.float32)
         S = np.zeros((self.K, self.K), np.float32)
         S_cold = np.zeros((self.K, self.K), np.float32) if cold else None

@@ -57,6 +57,8 @@ def _declare(lib):
         "dmt_assist_rows_bwd": (I, [P, L, L, P, P, P, P, P, P, P, P, P, L, I, I, P, P, P, P]),
         "dmt_assist_scratch_floats": (L, [I]),
         "dmt_assist_loss_grad": (I, [P, P, P, P, P, P, L, I, I, I, P, P, P, P, P]),
+        "dmt_assist_fit_work_floats": (L, [I, I, I]),
+        "dmt_assist_fit": (I, [P, P, P, P, L, I, I, I, P, I, I, F, I, I, I, P, P, P]),
         "dmt_base_fit": (I, [P, P, L, P, P, P]),
         "dmt_base_predict": (I, [P, P, C.c_int32, P, L, I, F, P, P, P]),
         "dmt_sort_segments_temp_bytes": (L, [L]),
@@ -214,6 +216,23 @@ def assist_rows_bwd(out, stride_e, stride_j, idx, rate, w, q, delta, seg, n, K, 
                                   ptr(perm), ptr(seg_key), ptr(seg_off), ptr(n_seg), n, K, n_rate, ptr(d_rate),
                                   ptr(d_w), ptr(scratch), stream()), "dmt_assist_rows_bwd")
     return d_rate, d_w
+
+
+def assist_fit(h, t, V, seg_off, params, ar_optim, aw_optim, loss_kind, lr=0.1, steps=10, max_iter=20, history=100,
+               work=None, scratch=None):
+    """Enqueue one owner's whole L-BFGS fit (dmt_assist_fit): params = [rate | w] on the device, updated in place; no
+    host synchronisation. Returns (work, scratch) so that the caller keeps them alive until the stream has run."""
+    lib = load()
+    K, n = V.shape
+    n_rate = params.numel() - K
+    if scratch is None:
+        scratch = torch.empty(lib.dmt_assist_scratch_floats(K), device=V.device, dtype=torch.float32)
+    if work is None:
+        work = torch.empty(lib.dmt_assist_fit_work_floats(n_rate, K, history), device=V.device, dtype=torch.float32)
+    check(lib.dmt_assist_fit(ptr(h), ptr(t), ptr(V), ptr(seg_off), n, n_rate, K, loss_kind, ptr(params),
+                             int(bool(ar_optim)), int(bool(aw_optim)), float(lr), int(steps), int(max_iter),
+                             int(history), ptr(work), ptr(scratch), stream()), "dmt_assist_fit")
+    return work, scratch
 
 
 def assist_loss_grad(h, t, V, seg_off, rate, w, loss_kind, scratch=None):

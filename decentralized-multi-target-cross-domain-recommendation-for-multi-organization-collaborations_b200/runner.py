@@ -163,6 +163,76 @@ def evaluate(assist, metric, logger, epoch):
     return {k: float(v) for k, v in logger.mean.items() if k.startswith('test/')}
 
 
+def joint_test_device(local_model, local_dataset, data_split, y_test, topk=10):
+    """The joint / alone drivers' test() loop (src/train_recsys_joint.py:153-199, src/train_recsys_alone.py:164-203) on
+    the device: every organization's local model (after ``models.distribute``) predicts its own block of the test
+    targets — ONE forward over all of the organization's test entries instead of one per 'test' batch — the predictions
+    are scattered into the global test CSR's storage order, and one `dmt_eval_blocks` launch produces the per-block
+    Loss / RMSE / NDCG@k sums with the reference's weighting (per-organization losses weighted by entry count ==
+    the global mean; RMSE / NDCG per block of `batch_size['test']` aligned rows over the organizations' concatenated
+    entries, weighted by the block's entry count). Returns {'test/Loss', 'test/RMSE' | 'test/NDCG'}.
+
+    local_dataset[i]['test'] is organization i's split (``.target`` = its columns of y_test); ae models take the
+    engine path instead (Organization.predict)."""
+    from . import engine as E
+    from . import native
+
+    dev = cfg['device']
+    mode = cfg['data_mode']
+    y = y_test.tocsr()
+    y.sort_indices()
+    n_cols = y.shape[1]
+    owner = np.full(n_cols, -1, np.int64)
+    local = np.zeros(n_cols, np.int64)
+    for i, sp in enumerate(data_split):
+        sp = np.asarray(sp, dtype=np.int64)
+        owner[sp] = i
+        local[sp] = np.arange(len(sp))
+    pred = torch.empty(y.nnz, device=dev)
+    rows_all = np.repeat(np.arange(y.shape[0], dtype=np.int64), np.diff(y.indptr))
+    with torch.no_grad():
+        for i, model in enumerate(local_model):
+            pos = np.flatnonzero(owner[y.indices] == i)
+            if pos.size == 0:
+                continue
+            model.train(False)
+            batch = {'target_' + mode: torch.from_numpy(rows_all[pos]).to(dev),
+                     'target_' + ('item' if mode == 'user' else 'user'): torch.from_numpy(local[y.indices[pos]]).to(dev),
+                     'target_rating': torch.from_numpy(y.data[pos].astype(np.float32)).to(dev)}
+            out = model(batch)
+            pred[torch.from_numpy(pos).to(dev)] = out['target_rating']
+    state = E.MtalState({'test': y}, [np.asarray(sp, dtype=np.int64) for sp in data_split], cfg['target_mode'], dev)
+    bs = cfg[cfg['model_name']]['batch_size']['test']
+    out = state.evaluate(pred, 'test', bs, topk)
+    if cfg['target_mode'] == 'implicit':
+        # The driver concatenates the organizations' batches with their LOCAL ids of the split entity and hands them to
+        # NDCG (src/train_recsys_joint.py:186-196), whose dense scatter `output_[user_idx, item_idx] = output`
+        # (src/metrics/metrics.py:66-76) keeps ONE entry per (aligned id, local id): on the CPU the last writer, i.e.
+        # the organization with the highest index. Same collapse here; block weights stay the uncollapsed entry counts
+        # (logger.append(evaluation, 'test', input_size)), the per-block mean runs over the aligned ids present.
+        n_local = max(len(sp) for sp in data_split)
+        key = rows_all * n_local + local[y.indices]
+        order = np.lexsort((owner[y.indices], key))           # by key, then organization
+        last = np.r_[key[order][1:] != key[order][:-1], True]  # highest organization of every key
+        win = order[last]                                      # ascending key == row-major, ascending local id
+        cnt = np.bincount(rows_all[win], minlength=y.shape[0])
+        ip = np.concatenate([[0], np.cumsum(cnt)])
+        edges = np.arange(0, y.shape[0] + bs, bs).clip(max=y.shape[0])
+        m_full = (y.indptr[edges[1:]] - y.indptr[edges[:-1]]).astype(np.float64)
+        rows_nz = np.add.reduceat(np.diff(ip) > 0, edges[:-1]).astype(np.float64)
+        loc_win = local[y.indices[win]]
+        k = np.array([min(topk, len(np.unique(loc_win[ip[a]:ip[b]]))) for a, b in zip(edges[:-1], edges[1:])], np.int32)
+        win_d = torch.from_numpy(win).to(dev)
+        tgt = torch.from_numpy(y.data.astype(np.float32)).to(dev)
+        sums = E.to_host(native.eval_blocks(E.to_dev(ip.astype(np.int32), dev), pred[win_d].contiguous(),
+                                            tgt[win_d].contiguous(), y.shape[0], bs, state.loss_kind,
+                                            E.to_dev(k, dev))).double().numpy()
+        ok = m_full > 0
+        w = m_full[ok] / m_full[ok].sum()
+        out['test/NDCG'] = float((sums[ok, 2] / rows_nz[ok] * w).sum())
+    return out
+
+
 def run_assist_experiment(data, control_name, seed=0, local_epochs=None, rounds=None, rng='device', keep_objects=False,
                           on_round=None):
     """Whole MTAL experiment through the drop-in API. Returns per-round global outputs and test metrics."""

@@ -73,6 +73,18 @@ int dmt_assist_loss_grad(const float* h, const float* t, const float* V, const i
                          const float* w, int64_t n, int n_rate, int K, int loss_kind, float* out_loss, float* d_rate,
                          float* d_w, float* scratch, void* stream);
 
+/* The whole L-BFGS fit of one owner's assisted learning rates / assistance weights (src/assist.py:118-129:
+ * `steps` x optimizer.step(closure) of torch.optim.LBFGS(lr, max_iter, history, no line search), src/utils.py:255-256)
+ * enqueued on `stream` without any host round trip: the closure is dmt_assist_loss_grad, the two-loop recursion, the
+ * step and torch's stopping rules (tolerance_grad 1e-7, tolerance_change 1e-9, max_eval = 5/4 max_iter) run in one
+ * single-block kernel per inner iteration; evaluations after a stopping rule skip themselves on a device flag.
+ * params = [rate (n_rate) | w (K)], initialised by the caller and updated in place; only the slices selected by
+ * ar_optim / aw_optim move. work >= dmt_assist_fit_work_floats(n_rate, K, history), scratch as dmt_assist_loss_grad. */
+int64_t dmt_assist_fit_work_floats(int n_rate, int K, int history);
+int dmt_assist_fit(const float* h, const float* t, const float* V, const int32_t* seg_off, int64_t n, int n_rate, int K,
+                   int loss_kind, float* params, int ar_optim, int aw_optim, float lr, int steps, int max_iter,
+                   int history, float* work, float* scratch, void* stream);
+
 /* models.Assist as a differentiable module (src/models/assist.py:25-40; the closure at src/assist.py:121-126 calls
  * loss.backward() through it). out is the [n x K] stack of the organizations' outputs addressed as
  * out[e*stride_e + j*stride_j]; target[e] = history[e] + rate[idx[e]] * sum_j softmax(w)_j out[e][j]; entries whose slot 0

@@ -135,6 +135,64 @@ def test_round_replay_vs_reference(dropin, case):
             assert abs(res["metrics"][t][name] - ref) <= 1e-4, (t, name, res["metrics"][t][name], ref)
 
 
+@pytest.mark.parametrize("case", cases("joint"))
+def test_joint_driver_loop_vs_reference(dropin, case):
+    """The joint driver's epoch (src/train_recsys_joint.py:93-97: train -> models.distribute -> test) with the drop-in
+    models on the GPU against what the reference's own loop produced (tests/golden/make_golden.py: case_joint): the
+    sampler orders of the fixture, the driver-owned clip_grad_norm_ + torch.optim.Adam, `models.distribute` into the 18
+    per-organization models, and the test() loop on the device (runner.joint_test_device). State after every epoch
+    <= 5e-4, logged test Loss <= 1e-5 relative, RMSE / NDCG <= 1e-4."""
+    models, _, _ = dropin
+    from dmtcdr_b200 import runner, synth
+    from dmtcdr_b200.config import cfg
+
+    fx = Fixture(case)
+    m = fx.meta
+    set_cfg(fx)
+    name = m["model_name"]
+    data = synth.make_rating_data("tiny-" + m["data_name"], seed=0)
+    dataset = runner.fetch_dataset(data)
+    runner.process_dataset(dataset)
+    K = m["num_organizations"]
+    data_split = [torch.from_numpy(fx["data_split/{}".format(i)]) for i in range(K)]
+    local_dataset = runner.make_split_dataset(dataset, data_split)
+    model = getattr(models, name)()
+    model.load_state_dict(fx.group("sd0"))
+    model = model.cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg[name]["lr"], betas=cfg[name]["betas"],
+                           weight_decay=cfg[name]["weight_decay"])
+    local_model = []
+    for i in range(K):
+        ds = local_dataset[i]["train"]
+        local_model.append(getattr(models, name)(ds.num_users["data"], ds.num_items["data"]).cuda())
+    gm = fx.json("metrics")
+    tr = dataset["train"]
+    for epoch in (1, 2):
+        rows = fx["e{}/rows".format(epoch)]
+        model.train(True)
+        s0 = 0
+        for n in fx["e{}/batch_sizes".format(epoch)]:
+            b = {k: v.cuda() for k, v in runner.pair_batch(tr, rows[s0:s0 + n]).items()}
+            s0 += int(n)
+            if len(b[cfg["data_mode"]]) == 0:
+                continue
+            opt.zero_grad()
+            out = model(b)
+            out["loss"].backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
+            opt.step()
+        for k, ref in fx.group("sd{}".format(epoch), as_torch=False).items():
+            assert rel_err(model.state_dict()[k].cpu().numpy(), ref) < 5e-4, (epoch, k)
+        models.distribute(model, local_model, data_split)
+        got = runner.joint_test_device(local_model, local_dataset, data_split, dataset["test"].target)
+        for key, val in got.items():
+            ref = gm[str(epoch)][key]
+            tol = 1e-5 * abs(ref) if key.endswith("Loss") else 1e-4
+            assert abs(val - ref) <= tol, (epoch, key, val, ref)
+    for k, ref in fx.group("local0_sd2", as_torch=False).items():
+        assert rel_err(local_model[0].state_dict()[k].cpu().numpy(), ref) < 5e-4, k
+
+
 def test_cpu_tensors_fail_loudly(dropin):
     """No CPU path: the models refuse host tensors instead of silently computing elsewhere."""
     models, _, _ = dropin

@@ -176,7 +176,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
@@ -323,13 +323,17 @@ def run_ours(args):
     def one_round(t):
         rounds.run_round(t, exchange)
 
+    # clocks / throttle reasons are sampled from the last warm-up round on (same load as the timed rounds), so that even a
+    # short timed region (8 GPUs: ~40 ms per round) has samples taken under load
+    sampler = ClockSampler(local) if rank == 0 else None
     for w in range(args.warmup):
+        if sampler and w == args.warmup - 1:
+            sampler.start()
         one_round(w + 1)
     rounds.sync()
     D.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
+    if sampler and not sampler.is_alive():
         sampler.start()
     launches0 = native.load().dmt_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,6 +391,9 @@ def run_ours(args):
 
     # ---- end to end through the drop-in API with host buffers (single-process API: measured on rank 0's GPU)
     e2e = run_e2e(args, data, rank, world, dev)
+    if world == 1:  # the same rounds with every organization's state_dict read back each round, as the reference does
+        eager = run_e2e(args, data, rank, world, dev, state_dicts=True, n_steps=2)
+        e2e["e2e_with_state_dicts"] = {k: eager[k] for k in ("value", "ms_per_step", "d2h_bytes_per_step", "state_dicts")}
 
     mf = run_mf_joint(data, dev) if (rank == 0 and world == 1) else None
     nmf = None
@@ -831,7 +838,7 @@ def run_config_block(control, data_name, dev, n_rounds=2, n_warm=2, local_epochs
     return out
 
 
-def run_e2e(args, data, rank, world, dev):
+def run_e2e(args, data, rank, world, dev, state_dicts=False, n_steps=None):
     """Rounds through the drop-in API (host scipy CSR in / out) on ALL ranks: with torch.distributed initialised the
     drop-in classes shard the organizations over the ranks themselves (Organization.train / predict do real work only
     for this rank's organizations, Assist.update all-gathers the prediction vectors over NCCL; dropin/assist.py), so
@@ -843,7 +850,7 @@ def run_e2e(args, data, rank, world, dev):
     from dmtcdr_b200.config import cfg
 
     E.XFER["h2d"] = E.XFER["d2h"] = 0
-    n_steps = max(1, min(args.steps, 3))
+    n_steps = n_steps or max(1, min(args.steps, 3))
     n_warm = 2  # round 1 captures/instantiates the epoch graphs; round 2 still grows allocator pools
     state = {}
     times = []
@@ -861,7 +868,7 @@ def run_e2e(args, data, rank, world, dev):
     t0 = time.perf_counter()
     state["t"] = t0
     res = runner.run_assist_experiment(data, CONTROL, seed=0, local_epochs=args.local_epochs, rounds=n_warm + n_steps,
-                                       rng="device", on_round=on_round)
+                                       rng="device", on_round=on_round, materialize_state_dicts=state_dicts)
     sec = D.max_over_ranks(sum(times) / len(times), dev)
     h2d = D.sum_over_ranks(float(E.XFER["h2d"]), dev)
     d2h = D.sum_over_ranks(float(E.XFER["d2h"]), dev)
@@ -873,6 +880,9 @@ def run_e2e(args, data, rank, world, dev):
                    "host scipy CSR in and out; organizations sharded over the ranks inside the drop-in classes, NCCL "
                    "all-gather inside Assist.update; bytes summed over ranks",
             "n_gpus_used": world, "rng": "device (device-drawn init/dropout: the production mode, not the parity mode)",
+            "state_dicts": "read back every round (the reference's per-round CPU copy, src/organization.py:177)"
+                           if state_dicts else "lazy: left on the device until read (the reference copies 18 x 4.3 MB "
+                                               "to the host every round; see e2e_with_state_dicts)",
             "rmse_last_round": res["metrics"][n_warm + n_steps].get("test/RMSE")}
 
 

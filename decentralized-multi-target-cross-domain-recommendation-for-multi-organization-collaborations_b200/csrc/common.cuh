@@ -100,4 +100,31 @@ __device__ __forceinline__ float loss_grad(int kind, float o, float y) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (PDL): a kernel launched with `pdl` may have its blocks scheduled while the previous
+// kernel of the stream is still draining; DMT_PDL_ENTRY() at the top of the kernel first lets the NEXT kernel do the
+// same and then waits until the previous kernel has completed and flushed its memory, so every load / store of the
+// body is ordered exactly as without PDL. What overlaps is launch latency and block scheduling (~2 us per edge of the
+// six-kernel step chain). Without the attribute both calls are no-ops.
+#define DMT_PDL_ENTRY()                            \
+    do {                                           \
+        cudaTriggerProgrammaticLaunchCompletion(); \
+        cudaGridDependencySynchronize();           \
+    } while (0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace dmt

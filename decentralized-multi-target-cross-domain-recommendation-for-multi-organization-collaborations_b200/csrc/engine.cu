@@ -81,6 +81,7 @@ struct dmt_org {
     int gather;      // fused step: 1 = weight / activation rows through bulk-copy rings (bulk.cuh), 0 = plain loads
     int bulk_blocks; // grid of the bulk decoder kernel (0: five per SM)
     int dec_form;    // register-load decoder of the fused step: 2 = four-warp blocks + next-chunk prefetch, 0 = eight warps
+    int pdl;         // fused step: same-stream kernels launched with programmatic stream serialization (common.cuh)
     int rows_mode;   // fused step, row kernels: 1 = W2 / W3 streamed through shared memory by bulk copies (fused_rows.cu)
     int rows_R;      // their row tile (fused_rows_per_cta)
     int fanout;  // 1: the backward pass of a step is enqueued as parallel branches (dmt_org_set_fanout)
@@ -376,15 +377,18 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     drop.p = 0.5f;
     drop.enabled = 1;
 #define WANT(cls) (only < 0 || only == (cls))
+    const bool pdl = only < 0 && o->pdl != 0;  // the per-class profiler measures plain launches
     if (WANT(K_ENC)) {
         FusedFwd f{br, o->rows_buf, o->d_indptr, o->d_indices, o->d_val, W1t, b1, o->W2t, b2, o->W3t, b3,
                    o->a1, o->a2, o->c, o->a3, drop};
-        if ((rc = o->rows_mode ? launch_fused_fwd_tma(f, B, o->rows_R, st) : launch_fused_fwd(f, B, st))) return rc;
+        if ((rc = o->rows_mode ? launch_fused_fwd_tma(f, B, o->rows_R, st, pdl) : launch_fused_fwd(f, B, st, pdl)))
+            return rc;
     }
     if (WANT(K_DEC)) {
         FusedDec d{br, o->dec_meta, o->t_batch_chunk, o->pt.batch_cnt, o->t_indices, o->t_val, o->t_inv_perm,
                    o->a3, W4, b4, o->g_sorted, o->dz3, o->loss_rows, o->dz_part, o->loss_part, o->row_cnt};
-        if ((rc = launch_fused_dec(d, o->gather ? o->bulk_blocks : o->dec_blocks, o->gather ? 1 : o->dec_form, st)))
+        if ((rc = launch_fused_dec(d, o->gather ? o->bulk_blocks : o->dec_blocks, o->gather ? 1 : o->dec_form, st,
+                                   pdl)))
             return rc;
     }
     // dW4 / db4 only has to be complete before the norm: it runs as a parallel branch of the captured step graph next
@@ -402,7 +406,8 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     }
     if (WANT(K_SEG_W1)) {
         FusedBwd w{br, o->pt.len, o->dz3, W3, W2, o->a1, o->a2, o->dz2, o->dz1, o->part_db, drop};
-        if ((rc = o->rows_mode ? launch_fused_bwd_rows_tma(w, B, o->rows_R, st) : launch_fused_bwd_rows(w, B, st)))
+        if ((rc = o->rows_mode ? launch_fused_bwd_rows_tma(w, B, o->rows_R, st, pdl)
+                               : launch_fused_bwd_rows(w, B, st, pdl)))
             return rc;
     }
     if (WANT(K_DENSE_BWD)) {
@@ -410,7 +415,7 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
                     o->part_dw, o->dw_cnt, o->rows_mode ? o->rows_R : kFusedRows};
         FusedSeg s{o->d_seg_meta, o->pd.batch_chunk_off, o->d_row_sorted, o->d_val_sorted, o->pd.part, o->pd.part_bias,
                    o->d_seg_cnt, o->active, b};
-        if ((rc = launch_fused_grad_phase(g, s, o->dz1, G + o->oW1, o->n_enc * 2, st))) return rc;
+        if ((rc = launch_fused_grad_phase(g, s, o->dz1, G + o->oW1, o->n_enc * 2, st, pdl))) return rc;
     }
     if (par) {  // join
         DMT_CUDA(cudaEventRecord(o->fev[1], sA));
@@ -418,11 +423,11 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     }
     if (WANT(K_NORM))
         if ((rc = launch_norm_prepare(G, o->n_params, o->partial, o->sc, o->step_dev, o->loss_rows, o->pt.len,
-                                      o->pt.batch_cnt + b, o->loss_buf + b, br, st)))
+                                      o->pt.batch_cnt + b, o->loss_buf + b, br, st, pdl)))
             return rc;
     if (WANT(K_ADAM))
         if ((rc = launch_adam_shadow(o->P, G, o->M, o->V, o->n_params, o->sc, hp, o->partial, o->step_dev, o->oW2,
-                                     o->oW3, o->W2t, o->W3t, st)))
+                                     o->oW3, o->W2t, o->W3t, st, pdl)))
             return rc;
 #undef WANT
     return 0;
@@ -693,6 +698,8 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
         o->gather = (env && strcmp(env, "bulk") == 0) ? 1 : 0;  // measured: per-row bulk copies are slower
         env = getenv("DMT_BULK_BLOCKS");
         o->bulk_blocks = env ? atoi(env) : 0;
+        env = getenv("DMT_PDL");
+        o->pdl = (env && atoi(env) != 0) ? 1 : 0;
         env = getenv("DMT_DEC_FORM");
         o->dec_form = (env && strcmp(env, "8w") == 0) ? 0 : 2;
         // Row kernels: weights through shared memory by bulk copies (fused_rows.cu) for small batches, where a row
@@ -785,6 +792,14 @@ int dmt_org_set_gather_mode(dmt_org_t* o, int mode) {
 }
 
 int dmt_org_gather_mode(const dmt_org_t* o) { return o ? o->gather : 0; }
+
+int dmt_org_set_pdl(dmt_org_t* o, int on) {
+    DMT_REQUIRE(o, "dmt_org_set_pdl: null");
+    on = on ? 1 : 0;
+    if (o->pdl != on) drop_graph(o);  // the launch attribute is baked into the captured graph
+    o->pdl = on;
+    return 0;
+}
 
 int dmt_org_set_fanout(dmt_org_t* o, int on) {
     DMT_REQUIRE(o, "dmt_org_set_fanout: null");

@@ -901,13 +901,25 @@ __device__ __forceinline__ void db_finish_body(const FusedGrad& p) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(256) ae_fwd_rows_kernel(FusedFwd p) { fwd_rows_body<kFusedRows>(p, blockIdx.x); }
+__global__ void __launch_bounds__(256) ae_fwd_rows_kernel(FusedFwd p) {
+    DMT_PDL_ENTRY();
+    fwd_rows_body<kFusedRows>(p, blockIdx.x);
+}
 
-__global__ void __launch_bounds__(256) ae_dec_chunks_kernel(FusedDec p) { dec_chunks_body(p); }
+__global__ void __launch_bounds__(256) ae_dec_chunks_kernel(FusedDec p) {
+    DMT_PDL_ENTRY();
+    dec_chunks_body(p);
+}
 
-__global__ void __launch_bounds__(128, 4) ae_dec_chunks4_kernel(FusedDec p) { dec_chunks4_body(p); }
+__global__ void __launch_bounds__(128, 4) ae_dec_chunks4_kernel(FusedDec p) {
+    DMT_PDL_ENTRY();
+    dec_chunks4_body(p);
+}
 
-__global__ void __launch_bounds__(kBulkWarps * 32) ae_dec_chunks_bulk_kernel(FusedDec p) { dec_chunks_bulk_body(p); }
+__global__ void __launch_bounds__(kBulkWarps * 32) ae_dec_chunks_bulk_kernel(FusedDec p) {
+    DMT_PDL_ENTRY();
+    dec_chunks_bulk_body(p);
+}
 
 __global__ void __launch_bounds__(kBulkWarps * 32) ae_seg_chunks_bulk_kernel(FusedSeg s, const float* src, float* grad,
                                                                              float* bias_grad) {
@@ -922,7 +934,10 @@ __global__ void __launch_bounds__(kBulkWarps * 32) ae_seg_chunks_bulk_kernel(Fus
 
 // 3a and 3b are separate kernels on parallel branches of the step graph: the row kernel keeps 64 weights per thread in
 // flight (~100 registers), the segment kernel needs 64 registers and four resident blocks per SM.
-__global__ void __launch_bounds__(256) ae_bwd_rows_kernel(FusedBwd p) { bwd_rows_body<kFusedRows>(p, blockIdx.x); }
+__global__ void __launch_bounds__(256) ae_bwd_rows_kernel(FusedBwd p) {
+    DMT_PDL_ENTRY();
+    bwd_rows_body<kFusedRows>(p, blockIdx.x);
+}
 
 __global__ void __launch_bounds__(256) ae_seg_chunks_kernel(FusedSeg s, const float* src, float* grad,
                                                             float* bias_grad) {
@@ -931,6 +946,7 @@ __global__ void __launch_bounds__(256) ae_seg_chunks_kernel(FusedSeg s, const fl
 }
 
 __global__ void __launch_bounds__(256) ae_grad_phase_kernel(FusedGrad p, FusedSeg s, const float* src, float* grad) {
+    DMT_PDL_ENTRY();
     const int blk = blockIdx.x;
     if (blk < 128) {
         dw_tile_body(p, blk);
@@ -952,6 +968,7 @@ __global__ void __launch_bounds__(256) norm_prepare_kernel(const float* __restri
                                                            const int32_t* t_len, const int32_t* n_targets_ptr,
                                                            float* loss_out, BatchRef br) {
     __shared__ float sh[32];
+    DMT_PDL_ENTRY();
     int lo, hi;
     if (!batch_range(br, lo, hi)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->active = 0;
@@ -991,6 +1008,7 @@ __global__ void __launch_bounds__(256) adam_shadow_kernel(float* __restrict__ w,
                                                           float* __restrict__ W2t, float* __restrict__ W3t) {
     __shared__ float sh[32];
     __shared__ float s_sc[3];
+    DMT_PDL_ENTRY();
     if (sc->active == 0) return;
     {
         float tot = 0.f;
@@ -1114,35 +1132,35 @@ __global__ void plan_sorted_kernel(const int32_t* __restrict__ perm, int64_t n, 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ launchers
-int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st) {
+int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st, bool pdl) {
     if (n_rows_max <= 0) return 0;
-    ae_fwd_rows_kernel<<<(n_rows_max + kFusedRows - 1) / kFusedRows, 256, 0, st>>>(p);
+    DMT_CUDA(launch_k(ae_fwd_rows_kernel, (n_rows_max + kFusedRows - 1) / kFusedRows, 256, 0, st, pdl, p));
     DMT_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st) {
+int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st, bool pdl) {
     if (gather == 1) {  // bulk-copy rings: five 128-thread blocks per SM
         const int blocks = blocks_hint > 0 ? blocks_hint : kNumSMs * 5;
-        ae_dec_chunks_bulk_kernel<<<blocks, kBulkWarps * 32, 0, st>>>(p);
+        DMT_CUDA(launch_k(ae_dec_chunks_bulk_kernel, blocks, kBulkWarps * 32, 0, st, pdl, p));
         DMT_LAUNCH_CHECK();
         return 0;
     }
     if (gather == 2) {  // four-warp blocks with next-chunk prefetch; blocks_hint counts 256-thread blocks
         const int blocks = blocks_hint > 0 ? blocks_hint * 2 : kNumSMs * 4;
-        ae_dec_chunks4_kernel<<<blocks, 128, 0, st>>>(p);
+        DMT_CUDA(launch_k(ae_dec_chunks4_kernel, blocks, 128, 0, st, pdl, p));
         DMT_LAUNCH_CHECK();
         return 0;
     }
     const int blocks = blocks_hint > 0 ? blocks_hint : kNumSMs * 2;
-    ae_dec_chunks_kernel<<<blocks, 256, 0, st>>>(p);
+    DMT_CUDA(launch_k(ae_dec_chunks_kernel, blocks, 256, 0, st, pdl, p));
     DMT_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st) {
+int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st, bool pdl) {
     if (n_rows_max <= 0) return 0;
-    ae_bwd_rows_kernel<<<(n_rows_max + kFusedRows - 1) / kFusedRows, 256, 0, st>>>(p);
+    DMT_CUDA(launch_k(ae_bwd_rows_kernel, (n_rows_max + kFusedRows - 1) / kFusedRows, 256, 0, st, pdl, p));
     DMT_LAUNCH_CHECK();
     return 0;
 }
@@ -1166,32 +1184,32 @@ int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, fl
 }
 
 int launch_fused_grad_phase(const FusedGrad& p, const FusedSeg& s, const float* src, float* grad, int n_chunk_max,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool pdl) {
     int seg_blocks = (n_chunk_max + 7) / 8;
     if (seg_blocks > kNumSMs) seg_blocks = kNumSMs;
     if (seg_blocks < 1) seg_blocks = 1;
-    ae_grad_phase_kernel<<<129 + seg_blocks, 256, 0, st>>>(p, s, src, grad);
+    DMT_CUDA(launch_k(ae_grad_phase_kernel, 129 + seg_blocks, 256, 0, st, pdl, p, s, src, grad));
     DMT_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_norm_prepare(const float* g, int64_t n, float* partial, AdamScalars* sc, int* step_dev,
                         const float* loss_rows, const int32_t* t_len, const int32_t* n_targets_ptr, float* loss_out,
-                        BatchRef br, cudaStream_t st) {
-    norm_prepare_kernel<<<kNormBlocks, 256, 0, st>>>(g, n, partial, sc, step_dev, loss_rows, t_len, n_targets_ptr,
-                                                     loss_out, br);
+                        BatchRef br, cudaStream_t st, bool pdl) {
+    DMT_CUDA(launch_k(norm_prepare_kernel, kNormBlocks, 256, 0, st, pdl, g, n, partial, sc, step_dev, loss_rows, t_len,
+                      n_targets_ptr, loss_out, br));
     DMT_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_adam_shadow(float* w, float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
                        const float* partial, const int* step_dev, int64_t oW2, int64_t oW3, float* W2t, float* W3t,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool pdl) {
     int64_t blocks = (n / 4 + 255) / 256;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     if (blocks < 1) blocks = 1;
-    adam_shadow_kernel<<<(int)blocks, 256, 0, st>>>(w, g, m, v, n, sc, hp, partial, kNormBlocks, step_dev, oW2, oW3,
-                                                    W2t, W3t);
+    DMT_CUDA(launch_k(adam_shadow_kernel, (int)blocks, 256, 0, st, pdl, w, g, m, v, n, sc, hp, partial, (int)kNormBlocks,
+                      step_dev, oW2, oW3, W2t, W3t));
     DMT_LAUNCH_CHECK();
     return 0;
 }

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(threads_for(R)) ae_fwd_rows_tma_kernel(FusedFw
     float(*cs)[H2c] = reinterpret_cast<float(*)[H2c]>(&a1s[R][0]);
     float* enc_part = ring + (kStages - 1) * kSlabFloats;  // ring slot 2, free until late_issue below
     static_assert(NW * H1c <= kSlabFloats, "encoder partials fit one ring slot");
+    DMT_PDL_ENTRY();
     int lo, hi;
     if (!batch_range(p.br, lo, hi)) return;
     const int m = hi - lo;
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(threads_for(R)) ae_bwd_rows_tma_kernel(FusedBw
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Smem<R>::kRing);
     float(*wide)[H1c] = reinterpret_cast<float(*)[H1c]>(reinterpret_cast<float*>(bars) + 16);  // dZ3, later dZ1
     float(*d2s)[H2c] = reinterpret_cast<float(*)[H2c]>(&wide[R][0]);
+    DMT_PDL_ENTRY();
     int lo, hi;
     if (!batch_range(p.br, lo, hi)) return;
     const int m = hi - lo;
@@ -419,37 +421,37 @@ int prepare_fused_rows() {
     return 0;
 }
 
-int launch_fused_fwd_tma(const FusedFwd& p, int n_rows_max, int R, cudaStream_t st) {
+int launch_fused_fwd_tma(const FusedFwd& p, int n_rows_max, int R, cudaStream_t st, bool pdl) {
     if (n_rows_max <= 0) return 0;
     const int grid = (n_rows_max + R - 1) / R;
     switch (R) {
         case 2:
-            ae_fwd_rows_tma_kernel<2><<<grid, threads_for(2), Smem<2>::bytes, st>>>(p);
+            DMT_CUDA(launch_k(ae_fwd_rows_tma_kernel<2>, grid, threads_for(2), Smem<2>::bytes, st, pdl, p));
             break;
         case 4:
-            ae_fwd_rows_tma_kernel<4><<<grid, threads_for(4), Smem<4>::bytes, st>>>(p);
+            DMT_CUDA(launch_k(ae_fwd_rows_tma_kernel<4>, grid, threads_for(4), Smem<4>::bytes, st, pdl, p));
             break;
         default:
             DMT_REQUIRE(R == 8, "launch_fused_fwd_tma: row tile must be 2, 4 or 8");
-            ae_fwd_rows_tma_kernel<8><<<grid, threads_for(8), Smem<8>::bytes, st>>>(p);
+            DMT_CUDA(launch_k(ae_fwd_rows_tma_kernel<8>, grid, threads_for(8), Smem<8>::bytes, st, pdl, p));
     }
     DMT_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_fused_bwd_rows_tma(const FusedBwd& p, int n_rows_max, int R, cudaStream_t st) {
+int launch_fused_bwd_rows_tma(const FusedBwd& p, int n_rows_max, int R, cudaStream_t st, bool pdl) {
     if (n_rows_max <= 0) return 0;
     const int grid = (n_rows_max + R - 1) / R;
     switch (R) {
         case 2:
-            ae_bwd_rows_tma_kernel<2><<<grid, threads_for(2), Smem<2>::bytes, st>>>(p);
+            DMT_CUDA(launch_k(ae_bwd_rows_tma_kernel<2>, grid, threads_for(2), Smem<2>::bytes, st, pdl, p));
             break;
         case 4:
-            ae_bwd_rows_tma_kernel<4><<<grid, threads_for(4), Smem<4>::bytes, st>>>(p);
+            DMT_CUDA(launch_k(ae_bwd_rows_tma_kernel<4>, grid, threads_for(4), Smem<4>::bytes, st, pdl, p));
             break;
         default:
             DMT_REQUIRE(R == 8, "launch_fused_bwd_rows_tma: row tile must be 2, 4 or 8");
-            ae_bwd_rows_tma_kernel<8><<<grid, threads_for(8), Smem<8>::bytes, st>>>(p);
+            DMT_CUDA(launch_k(ae_bwd_rows_tma_kernel<8>, grid, threads_for(8), Smem<8>::bytes, st, pdl, p));
     }
     DMT_LAUNCH_CHECK();
     return 0;

@@ -224,25 +224,25 @@ struct FusedPlanArgs {
     int4* dec_meta;
     FusedPlanSide t, d;
 };
-int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st);
+int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st, bool pdl = false);
 // gather: 0 = rows through registers (plain loads), 1 = rows through shared-memory rings (bulk copies, bulk.cuh)
-int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st);
+int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st, bool pdl = false);
 // fused_rows.cu: the row kernels with W2 / W3 streamed through shared memory by 32 KB bulk copies; R = rows per CTA
 int fused_rows_per_cta(int batch_rows);
 int prepare_fused_rows();
-int launch_fused_fwd_tma(const FusedFwd& p, int n_rows_max, int R, cudaStream_t st);
-int launch_fused_bwd_rows_tma(const FusedBwd& p, int n_rows_max, int R, cudaStream_t st);
-int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st);
+int launch_fused_fwd_tma(const FusedFwd& p, int n_rows_max, int R, cudaStream_t st, bool pdl = false);
+int launch_fused_bwd_rows_tma(const FusedBwd& p, int n_rows_max, int R, cudaStream_t st, bool pdl = false);
+int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st, bool pdl = false);
 int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, float* bias_grad, int n_chunk_max,
                             int gather, cudaStream_t st);
 int launch_fused_grad_phase(const FusedGrad& p, const FusedSeg& s, const float* src, float* grad, int n_chunk_max,
-                            cudaStream_t st);
+                            cudaStream_t st, bool pdl = false);
 int launch_norm_prepare(const float* g, int64_t n, float* partial, AdamScalars* sc, int* step_dev,
                         const float* loss_rows, const int32_t* t_len, const int32_t* n_targets_ptr, float* loss_out,
-                        BatchRef br, cudaStream_t st);
+                        BatchRef br, cudaStream_t st, bool pdl = false);
 int launch_adam_shadow(float* w, float* g, float* m, float* v, int64_t n, const AdamScalars* sc, AdamHyper hp,
                        const float* partial, const int* step_dev, int64_t oW2, int64_t oW3, float* W2t, float* W3t,
-                       cudaStream_t st);
+                       cudaStream_t st, bool pdl = false);
 int launch_shadow_refresh(const float* W2, const float* W3, float* W2t, float* W3t, cudaStream_t st);
 int launch_plan_fused(const FusedPlanArgs& a, cudaStream_t st);
 

@@ -88,6 +88,7 @@ def _declare(lib):
         "dmt_org_set_fanout": (I, [P, I]),
         "dmt_org_set_decoder_blocks": (I, [P, I]),
         "dmt_org_set_gather_mode": (I, [P, I]),
+        "dmt_org_set_pdl": (I, [P, I]),
         "dmt_org_gather_mode": (I, [P]),
         "dmt_org_set_step_mode": (I, [P, I]),
         "dmt_org_step_mode": (I, [P]),
@@ -580,6 +581,10 @@ class Org:
     def set_decoder_blocks(self, blocks):
         """Grid of the decoder chunk kernel (0: two blocks per SM); fewer blocks pay with many organizations per GPU."""
         check(self._lib.dmt_org_set_decoder_blocks(self.h, int(blocks)), "dmt_org_set_decoder_blocks")
+
+    def set_pdl(self, on):
+        """Programmatic dependent launch between the kernels of the fused step (dmt_org_set_pdl)."""
+        check(self._lib.dmt_org_set_pdl(self.h, int(bool(on))), "dmt_org_set_pdl")
 
     def set_gather_mode(self, mode):
         """'ldg' (register loads, default) or 'bulk' (one cp.async.bulk copy per row into shared-memory rings,

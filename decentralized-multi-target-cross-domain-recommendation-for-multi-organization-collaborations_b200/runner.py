@@ -234,8 +234,11 @@ def joint_test_device(local_model, local_dataset, data_split, y_test, topk=10):
 
 
 def run_assist_experiment(data, control_name, seed=0, local_epochs=None, rounds=None, rng='device', keep_objects=False,
-                          on_round=None):
-    """Whole MTAL experiment through the drop-in API. Returns per-round global outputs and test metrics."""
+                          on_round=None, materialize_state_dicts=False):
+    """Whole MTAL experiment through the drop-in API. Returns per-round global outputs and test metrics.
+    materialize_state_dicts: read every organization's state_dict at the end of every round, as the reference's
+    per-round checkpoint of whole objects does (src/train_recsys_assist.py:87-89; src/organization.py:177 copies them
+    to the CPU in train()); by default they stay on the device until somebody reads them."""
     make_cfg(control_name, device='cuda', seed=seed)
     cfg['dmt_rng'] = rng
     if local_epochs is not None:
@@ -273,6 +276,11 @@ def run_assist_experiment(data, control_name, seed=0, local_epochs=None, rounds=
         outs = [{k: organization[i].predict(dataset[i][k], t) for k in dataset[i]} for i in range(len(dataset))]
         tm.append(time.perf_counter())
         assist.update(outs, t)
+        if materialize_state_dicts:
+            for o in organization:
+                sd = o.model_state_dict[t]
+                if sd is not None:
+                    len(sd)
         tm.append(time.perf_counter())
         metrics[t] = evaluate(assist, metric, logger, t)
         tm.append(time.perf_counter())

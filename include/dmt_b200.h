@@ -290,6 +290,11 @@ int dmt_org_set_decoder_blocks(dmt_org_t* org, int blocks);
  * grid (decoder 28-45 us against 23 us at ML1M shape: the copy engine's per-operation cost dominates at 1 KB), kept
  * as the measured alternative. Same sums in a different fixed order. */
 int dmt_org_set_gather_mode(dmt_org_t* org, int mode);
+/* on = 1: the same-stream kernels of the fused step are launched with programmatic stream serialization (PDL): a
+ * kernel's blocks are scheduled while its predecessor drains and wait at cudaGridDependencySynchronize before touching
+ * memory, which hides launch latency between the six dependent launches of a batch (src/organization.py:149-162 is a
+ * strictly sequential loop). Pays on ranks with few organizations; default off (DMT_PDL=1). Results are unchanged. */
+int dmt_org_set_pdl(dmt_org_t* org, int on);
 int dmt_org_gather_mode(const dmt_org_t* org);
 /* How one iteration of the batch loop (src/organization.py:149-162) is cut into launches. mode 1 (default whenever
  * H1 = 256, H2 = 128, batch_rows <= 512 and decoder mode 0): the fused step of csrc/fused.cu — six dependent launches

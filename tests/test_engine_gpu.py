@@ -193,7 +193,7 @@ def chunk_census(T, batches, dec_chunk=128, seg_chunk=64):
     return multi_rows, multi_segs
 
 
-@pytest.mark.parametrize("mode", ["epoch", "epoch_fanout", "round"])
+@pytest.mark.parametrize("mode", ["epoch", "epoch_fanout", "round", "round_pdl"])
 @pytest.mark.parametrize("decoder", ["gather", "gather_bulk", "gather_classic", "tc"])
 @pytest.mark.parametrize("shape", ["ml1m_batch", "zipf_wide"])
 def test_train_benchmark_shape(nat, shape, decoder, mode):
@@ -227,7 +227,10 @@ def test_train_benchmark_shape(nat, shape, decoder, mode):
     ref_p, ref_losses = train.train_org_ae(p0, D, T, "user", "explicit", epoch_batches, masks)
     d_csr = (cu(D.indptr, torch.int32), cu(D.indices, torch.int32), cu(D.data))
     t_csr = (cu(T.indptr, torch.int32), cu(T.indices, torch.int32))
-    org = nat.Org(n_rows, n_enc, n_dec, 256, 128, d_csr, t_csr, bs, 0, plan_epochs=n_epochs if mode == "round" else 1)
+    # "round_pdl": whole-round plan with the step's kernels launched with programmatic stream serialization
+    org = nat.Org(n_rows, n_enc, n_dec, 256, 128, d_csr, t_csr, bs, 0,
+                  plan_epochs=n_epochs if mode.startswith("round") else 1)
+    org.set_pdl(mode == "round_pdl")
     # "gather": the fused six-launch step (csrc/fused.cu, the default); "gather_bulk": the same step with the gathered
     # rows travelling through bulk-copy rings (csrc/bulk.cuh); "gather_classic": one kernel per layer
     want_fused = decoder in ("gather", "gather_bulk")
@@ -245,7 +248,7 @@ def test_train_benchmark_shape(nat, shape, decoder, mode):
     tval = cu(T.data)
     org.set_target(tval)
     nb = len(epoch_batches[0])
-    if mode == "round":
+    if mode.startswith("round"):
         rows_a = np.concatenate([np.concatenate(b) for b in epoch_batches])
         off = np.concatenate([[0], np.cumsum([len(r) for b in epoch_batches for r in b])])
         keep = torch.cat([k for ke in keep_epochs for k in ke]).to(torch.uint8).cuda()

@@ -84,6 +84,7 @@ struct dmt_org {
     int pdl;         // fused step: same-stream kernels launched with programmatic stream serialization (common.cuh)
     int rows_mode;   // fused step, row kernels: 1 = W2 / W3 streamed through shared memory by bulk copies (fused_rows.cu)
     int rows_R;      // their row tile (fused_rows_per_cta)
+    int stream_R;    // row tile of the register-streamed row kernels (4, 8 or 16)
     int fanout;  // 1: the backward pass of a step is enqueued as parallel branches (dmt_org_set_fanout)
     float* tc_scratch;  // split-K partials [splits x batch_rows x H1], then per-tile loss sums
     // tables of per-row CSR windows at 128-column tile borders, one per target CSR seen (train targets, predict splits)
@@ -381,7 +382,8 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     if (WANT(K_ENC)) {
         FusedFwd f{br, o->rows_buf, o->d_indptr, o->d_indices, o->d_val, W1t, b1, o->W2t, b2, o->W3t, b3,
                    o->a1, o->a2, o->c, o->a3, drop};
-        if ((rc = o->rows_mode ? launch_fused_fwd_tma(f, B, o->rows_R, st, pdl) : launch_fused_fwd(f, B, st, pdl)))
+        if ((rc = o->rows_mode ? launch_fused_fwd_tma(f, B, o->rows_R, st, pdl)
+                               : launch_fused_fwd(f, B, st, pdl, o->stream_R)))
             return rc;
     }
     if (WANT(K_DEC)) {
@@ -407,12 +409,12 @@ static int enqueue_step_fused(dmt_org* o, int b, bool use_keep, AdamHyper hp, in
     if (WANT(K_SEG_W1)) {
         FusedBwd w{br, o->pt.len, o->dz3, W3, W2, o->a1, o->a2, o->dz2, o->dz1, o->part_db, drop};
         if ((rc = o->rows_mode ? launch_fused_bwd_rows_tma(w, B, o->rows_R, st, pdl)
-                               : launch_fused_bwd_rows(w, B, st, pdl)))
+                               : launch_fused_bwd_rows(w, B, st, pdl, o->stream_R)))
             return rc;
     }
     if (WANT(K_DENSE_BWD)) {
         FusedGrad g{br, o->pt.len, o->dz3, o->dz2, o->c, o->a1, o->part_db, G, o->oW2, o->oW3, o->ob1, o->ob2, o->ob3,
-                    o->part_dw, o->dw_cnt, o->rows_mode ? o->rows_R : kFusedRows};
+                    o->part_dw, o->dw_cnt, o->rows_mode ? o->rows_R : o->stream_R};
         FusedSeg s{o->d_seg_meta, o->pd.batch_chunk_off, o->d_row_sorted, o->d_val_sorted, o->pd.part, o->pd.part_bias,
                    o->d_seg_cnt, o->active, b};
         if ((rc = launch_fused_grad_phase(g, s, o->dz1, G + o->oW1, o->n_enc * 2, st, pdl))) return rc;
@@ -710,6 +712,9 @@ int dmt_org_create(dmt_org_t** out, int n_rows, int n_enc, int n_dec, int H1, in
         o->rows_R = fused_rows_per_cta(batch_rows);
         o->rows_mode = o->rows_R < 8 ? 1 : 0;
         if (env) o->rows_mode = strcmp(env, "tma") == 0 ? 1 : 0;
+        env = getenv("DMT_STREAM_ROWS");
+        o->stream_R = env ? atoi(env) : kFusedRows;
+        if (o->stream_R != 4 && o->stream_R != 16) o->stream_R = kFusedRows;
     }
     A(dalloc(&o->tc_scratch, decoder_tc_scratch_floats(batch_rows, n_dec, H1)));
     A(dalloc(&o->gbuf, t_cap)); A(dalloc(&o->dval_ord, d_cap)); A(dalloc(&o->row_batch, o->rows_cap + 1));
@@ -792,6 +797,14 @@ int dmt_org_set_gather_mode(dmt_org_t* o, int mode) {
 }
 
 int dmt_org_gather_mode(const dmt_org_t* o) { return o ? o->gather : 0; }
+
+int dmt_org_set_row_tile(dmt_org_t* o, int rows) {
+    DMT_REQUIRE(o && (rows == 4 || rows == 8 || rows == 16), "dmt_org_set_row_tile: rows must be 4, 8 or 16");
+    if (getenv("DMT_STREAM_ROWS") != nullptr) return 0;  // an explicit environment choice wins (A/B runs)
+    if (o->stream_R != rows) drop_graph(o);  // grid and kernel instance are baked into the captured graph
+    o->stream_R = rows;
+    return 0;
+}
 
 int dmt_org_set_pdl(dmt_org_t* o, int on) {
     DMT_REQUIRE(o, "dmt_org_set_pdl: null");

@@ -90,13 +90,22 @@ __device__ __forceinline__ void fwd_rows_body(const FusedFwd& p, int cta) {
     const int r0 = cta * R;
     if (r0 >= m) return;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    // ---- encoder: one warp per row, every lane owns 2 float4 slices of the 256 hidden units
-    for (int r = wid; r < R; r += 8) {
+    // ---- encoder: every lane owns 2 float4 slices of the 256 hidden units; a row's data entries are split over
+    //      WPR = 8 / R warps when the tile has fewer rows than the block has warps (the longest row of the tile bounds
+    //      this phase: ~100 entries at ML1M shape), eight 1 KB weight rows in flight per warp
+    constexpr int WPR = R >= 8 ? 1 : 8 / R;
+    __shared__ __align__(16) float encp[WPR > 1 ? (WPR - 1) * R : 1][H1c];
+    for (int rb = 0; rb < (R > 8 ? R : 8); rb += 8) {
+        const int r = WPR > 1 ? wid % R : rb + wid;
+        const int part = WPR > 1 ? wid / R : 0;
+        if (r >= R) break;
         float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
         const bool valid = r0 + r < m;
         if (valid) {
             const int u = p.rows[lo + r0 + r];
-            const int e0 = p.d_indptr[u], e1 = p.d_indptr[u + 1];
+            const int eA = p.d_indptr[u], eB = p.d_indptr[u + 1];
+            const int per = (eB - eA + WPR - 1) / WPR;
+            const int e0 = eA + part * per, e1 = min(eB, e0 + per);
             for (int eb = e0; eb < e1; eb += 32) {
                 const int e = eb + lane;
                 int c_l = 0;
@@ -106,11 +115,11 @@ __device__ __forceinline__ void fwd_rows_body(const FusedFwd& p, int cta) {
                     v_l = p.d_val[e];
                 }
                 const int cnt = min(32, e1 - eb);
-                for (int i = 0; i < cnt; i += 4) {  // four 1 KB weight rows in flight; slots past cnt weigh 0
-                    float vv[4];
-                    float4 w0[4], w1[4];
+                for (int i = 0; i < cnt; i += 8) {  // slots past cnt weigh 0
+                    float vv[8];
+                    float4 w0[8], w1[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 8; ++q) {
                         const int src = min(i + q, cnt - 1);
                         const int col = __shfl_sync(0xffffffffu, c_l, src);
                         const float v = __shfl_sync(0xffffffffu, v_l, src);
@@ -120,12 +129,27 @@ __device__ __forceinline__ void fwd_rows_body(const FusedFwd& p, int cta) {
                         w1[q] = ld4(wr + 128);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 8; ++q) {
                         fma4(acc0, vv[q], w0[q]);
                         fma4(acc1, vv[q], w1[q]);
                     }
                 }
             }
+        }
+        if constexpr (WPR > 1) {
+            if (part > 0) {
+                st4(&encp[(part - 1) * R + r][lane * 4], acc0);
+                st4(&encp[(part - 1) * R + r][128 + lane * 4], acc1);
+            }
+            __syncthreads();
+            if (part > 0) break;
+#pragma unroll
+            for (int q = 1; q < WPR; ++q) {  // a row's partials are added in warp order
+                add4(acc0, ld4(&encp[(q - 1) * R + r][lane * 4]));
+                add4(acc1, ld4(&encp[(q - 1) * R + r][128 + lane * 4]));
+            }
+        }
+        if (valid) {
             const float4 bb0 = ld4(p.b1 + lane * 4), bb1 = ld4(p.b1 + 128 + lane * 4);
             acc0 = make_float4(tanhf(acc0.x + bb0.x), tanhf(acc0.y + bb0.y), tanhf(acc0.z + bb0.z), tanhf(acc0.w + bb0.w));
             acc1 = make_float4(tanhf(acc1.x + bb1.x), tanhf(acc1.y + bb1.y), tanhf(acc1.z + bb1.z), tanhf(acc1.w + bb1.w));
@@ -901,9 +925,10 @@ __device__ __forceinline__ void db_finish_body(const FusedGrad& p) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+template <int R>
 __global__ void __launch_bounds__(256) ae_fwd_rows_kernel(FusedFwd p) {
     DMT_PDL_ENTRY();
-    fwd_rows_body<kFusedRows>(p, blockIdx.x);
+    fwd_rows_body<R>(p, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256) ae_dec_chunks_kernel(FusedDec p) {
@@ -934,9 +959,10 @@ __global__ void __launch_bounds__(kBulkWarps * 32) ae_seg_chunks_bulk_kernel(Fus
 
 // 3a and 3b are separate kernels on parallel branches of the step graph: the row kernel keeps 64 weights per thread in
 // flight (~100 registers), the segment kernel needs 64 registers and four resident blocks per SM.
+template <int R>
 __global__ void __launch_bounds__(256) ae_bwd_rows_kernel(FusedBwd p) {
     DMT_PDL_ENTRY();
-    bwd_rows_body<kFusedRows>(p, blockIdx.x);
+    bwd_rows_body<R>(p, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256) ae_seg_chunks_kernel(FusedSeg s, const float* src, float* grad,
@@ -1132,9 +1158,17 @@ __global__ void plan_sorted_kernel(const int32_t* __restrict__ perm, int64_t n, 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ launchers
-int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st, bool pdl) {
+int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st, bool pdl, int R) {
     if (n_rows_max <= 0) return 0;
-    DMT_CUDA(launch_k(ae_fwd_rows_kernel, (n_rows_max + kFusedRows - 1) / kFusedRows, 256, 0, st, pdl, p));
+    const int grid = (n_rows_max + R - 1) / R;
+    if (R == 4) {
+        DMT_CUDA(launch_k(ae_fwd_rows_kernel<4>, grid, 256, 0, st, pdl, p));
+    } else if (R == 16) {
+        DMT_CUDA(launch_k(ae_fwd_rows_kernel<16>, grid, 256, 0, st, pdl, p));
+    } else {
+        DMT_REQUIRE(R == kFusedRows, "launch_fused_fwd: row tile must be 4, 8 or 16");
+        DMT_CUDA(launch_k(ae_fwd_rows_kernel<kFusedRows>, grid, 256, 0, st, pdl, p));
+    }
     DMT_LAUNCH_CHECK();
     return 0;
 }
@@ -1158,9 +1192,17 @@ int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_
     return 0;
 }
 
-int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st, bool pdl) {
+int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st, bool pdl, int R) {
     if (n_rows_max <= 0) return 0;
-    DMT_CUDA(launch_k(ae_bwd_rows_kernel, (n_rows_max + kFusedRows - 1) / kFusedRows, 256, 0, st, pdl, p));
+    const int grid = (n_rows_max + R - 1) / R;
+    if (R == 4) {
+        DMT_CUDA(launch_k(ae_bwd_rows_kernel<4>, grid, 256, 0, st, pdl, p));
+    } else if (R == 16) {
+        DMT_CUDA(launch_k(ae_bwd_rows_kernel<16>, grid, 256, 0, st, pdl, p));
+    } else {
+        DMT_REQUIRE(R == kFusedRows, "launch_fused_bwd_rows: row tile must be 4, 8 or 16");
+        DMT_CUDA(launch_k(ae_bwd_rows_kernel<kFusedRows>, grid, 256, 0, st, pdl, p));
+    }
     DMT_LAUNCH_CHECK();
     return 0;
 }

@@ -224,7 +224,7 @@ struct FusedPlanArgs {
     int4* dec_meta;
     FusedPlanSide t, d;
 };
-int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st, bool pdl = false);
+int launch_fused_fwd(const FusedFwd& p, int n_rows_max, cudaStream_t st, bool pdl = false, int R = kFusedRows);
 // gather: 0 = rows through registers (plain loads), 1 = rows through shared-memory rings (bulk copies, bulk.cuh)
 int launch_fused_dec(const FusedDec& p, int blocks_hint, int gather, cudaStream_t st, bool pdl = false);
 // fused_rows.cu: the row kernels with W2 / W3 streamed through shared memory by 32 KB bulk copies; R = rows per CTA
@@ -232,7 +232,7 @@ int fused_rows_per_cta(int batch_rows);
 int prepare_fused_rows();
 int launch_fused_fwd_tma(const FusedFwd& p, int n_rows_max, int R, cudaStream_t st, bool pdl = false);
 int launch_fused_bwd_rows_tma(const FusedBwd& p, int n_rows_max, int R, cudaStream_t st, bool pdl = false);
-int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st, bool pdl = false);
+int launch_fused_bwd_rows(const FusedBwd& p, int n_rows_max, cudaStream_t st, bool pdl = false, int R = kFusedRows);
 int launch_fused_seg_chunks(const FusedSeg& s, const float* src, float* grad, float* bias_grad, int n_chunk_max,
                             int gather, cudaStream_t st);
 int launch_fused_grad_phase(const FusedGrad& p, const FusedSeg& s, const float* src, float* grad, int n_chunk_max,

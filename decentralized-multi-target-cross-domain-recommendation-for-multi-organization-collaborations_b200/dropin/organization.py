@@ -314,6 +314,7 @@ class Organization:
             n_orgs = self.__dict__.get('_orgs_on_rank') or (
                 int(cfg['num_organizations']) if 'num_organizations' in cfg else 1)
             self._eng.h.set_decoder_blocks(_rl.decoder_blocks_for(n_orgs))
+            self._eng.h.set_row_tile(_rl.row_tile_for(n_orgs))
             # few organizations on this GPU: a step's backward pass runs as parallel graph branches (roundloop.py)
             fan = E.os.environ.get('DMT_FANOUT')
             self._eng.h.set_fanout((n_orgs <= _rl.FANOUT_MAX_ORGS) if fan is None else fan == '1')

@@ -89,6 +89,7 @@ def _declare(lib):
         "dmt_org_set_decoder_blocks": (I, [P, I]),
         "dmt_org_set_gather_mode": (I, [P, I]),
         "dmt_org_set_pdl": (I, [P, I]),
+        "dmt_org_set_row_tile": (I, [P, I]),
         "dmt_org_gather_mode": (I, [P]),
         "dmt_org_set_step_mode": (I, [P, I]),
         "dmt_org_step_mode": (I, [P]),
@@ -582,6 +583,10 @@ class Org:
         """Grid of the decoder chunk kernel (0: two blocks per SM); fewer blocks pay with many organizations per GPU."""
         check(self._lib.dmt_org_set_decoder_blocks(self.h, int(blocks)), "dmt_org_set_decoder_blocks")
 
+    def set_row_tile(self, rows):
+        """Batch rows per CTA of the fused step's row kernels (dmt_org_set_row_tile): 4 for ranks with few organizations."""
+        check(self._lib.dmt_org_set_row_tile(self.h, int(rows)), "dmt_org_set_row_tile")
+
     def set_pdl(self, on):
         """Programmatic dependent launch between the kernels of the fused step (dmt_org_set_pdl)."""
         check(self._lib.dmt_org_set_pdl(self.h, int(bool(on))), "dmt_org_set_pdl")
@@ -620,12 +625,16 @@ class Org:
     def train_epoch(self, rows, row_off, n_t_entries, n_d_entries, keep=None, seed=0, lr=1e-3, betas=(0.9, 0.999),
                     eps=1e-8, weight_decay=5e-4, max_norm=1.0, epoch_loss=None):
         nb = row_off.numel() - 1
+        # the row lists, masks and loss buffer were usually produced on torch's current stream just before this call:
+        # order the organization's stream behind it (a fill kernel of `epoch_loss` landing after the epoch would erase it)
+        self.wait_current()
         check(self._lib.dmt_org_train_epoch(self.h, ptr(rows), ptr(row_off), rows.numel(), nb, int(n_t_entries),
                                             int(n_d_entries), ptr(keep), int(seed), float(lr), float(betas[0]),
                                             float(betas[1]), float(eps), float(weight_decay), float(max_norm),
                                             ptr(epoch_loss)), "dmt_org_train_epoch")
 
     def predict(self, d_csr, t_csr, n_rows, out):
+        self.wait_current()  # `out` and the CSR arrays may still be in flight on torch's current stream
         check(self._lib.dmt_org_predict(self.h, ptr(d_csr[0]), ptr(d_csr[1]), ptr(d_csr[2]), ptr(t_csr[0]),
                                         ptr(t_csr[1]), n_rows, ptr(out)), "dmt_org_predict")
         return out

@@ -295,6 +295,13 @@ int dmt_org_set_gather_mode(dmt_org_t* org, int mode);
  * memory, which hides launch latency between the six dependent launches of a batch (src/organization.py:149-162 is a
  * strictly sequential loop). Pays on ranks with few organizations; default off (DMT_PDL=1). Results are unchanged. */
 int dmt_org_set_pdl(dmt_org_t* org, int on);
+/* Batch rows per CTA of the row-local forward / backward kernels of the fused step at 500-row batches (4, 8 or 16;
+ * default 8). With 4 rows per CTA two warps share every row's encoder entries and the per-CTA dense work halves: the
+ * kernels take 14 / 12 us instead of 19 / 16 us (ML1M shape), which shortens the round of a rank that holds <= 3
+ * organizations (28.6 vs 30.5 ms) and lengthens it when more organizations share the GPU (twice the CTAs and weight
+ * traffic: 18 organizations 205.7 vs 197.7 ms). Same arithmetic; the encoder sum of a row is split in two ordered
+ * halves. */
+int dmt_org_set_row_tile(dmt_org_t* org, int rows);
 int dmt_org_gather_mode(const dmt_org_t* org);
 /* How one iteration of the batch loop (src/organization.py:149-162) is cut into launches. mode 1 (default whenever
  * H1 = 256, H2 = 128, batch_rows <= 512 and decoder mode 0): the fused step of csrc/fused.cu — six dependent launches

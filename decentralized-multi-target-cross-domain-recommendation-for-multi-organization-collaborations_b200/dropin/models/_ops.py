@@ -35,9 +35,12 @@ def sorted_segments(idx, bound):
     return seg
 
 
-def _scaled(t, dloss, n):
-    """t * dloss / n without reading dloss on the host (float(dloss) would drain the stream every step)."""
-    return None if t is None else t * (dloss / n)
+def _scaled(t, f, inplace=True):
+    """t * f with f = dloss / n a device scalar: no host read of dloss (float(dloss) would drain the stream every
+    step). Fresh gradient buffers are scaled in place."""
+    if t is None:
+        return None
+    return t.mul_(f) if inplace else t * f
 
 
 def batch_csr(row_ids, cols, vals, rows_sorted):
@@ -177,9 +180,10 @@ class MFFn(torch.autograd.Function):
         dWi, dbi = native.mf_bwd_table(user, Wu, bu, pi, dpred, 1.0, seg_i, Wi.shape[0])
         dpu = native.mf_bwd_side(user, Wu, bu, dpred, 1.0) if pu is not None else None
         dpi = native.mf_bwd_side(item, Wi, bi, dpred, 1.0) if pi is not None else None
-        sc = lambda t: _scaled(t, dloss, n)  # noqa: E731
-        return (None, None, None, sc(dWu), sc(dWi), sc(dbu).view(-1, 1), sc(dbi).view(-1, 1), sc(sums[1]).reshape(1),
-                sc(dpu), sc(dpi), None)
+        f = dloss / n
+        sc = lambda t: _scaled(t, f)  # noqa: E731
+        return (None, None, None, sc(dWu), sc(dWi), sc(dbu).view(-1, 1), sc(dbi).view(-1, 1),
+                _scaled(sums[1], f, False).reshape(1), sc(dpu), sc(dpi), None)
 
 
 class EmbedCatFn(torch.autograd.Function):
@@ -243,9 +247,10 @@ class GMFLossFn(torch.autograd.Function):
         dpu = native.mf_bwd_side(user, Wu, bu, dpred, 1.0, cs) if pu is not None else None
         dpi = native.mf_bwd_side(item, Wi, bi, dpred, 1.0, cs) if pi is not None else None
         dcs = native.weighted_colsum(dpred, q, 1.0)
-        sc = lambda t: _scaled(t, dloss, n)  # noqa: E731
+        f = dloss / n
+        sc = lambda t: _scaled(t, f)  # noqa: E731
         return (None, None, None, sc(dWu), sc(dWi), sc(dbu).view(-1, 1), sc(dbi).view(-1, 1), sc(dpu), sc(dpi), sc(dcs),
-                sc(dpred), None)
+                _scaled(dpred, f, False), None)
 
 
 class LossFn(torch.autograd.Function):

@@ -17,6 +17,11 @@ else:
     data, dataset, data_split, mats, cfg = bench.build_problem()
     R = roundloop.AssistRounds(mats, [s.numpy() for s in data_split], "explicit", 500, local_epochs=1, rank=0, world=18,
                                device="cuda:0")
+    # one organization is enough for a capture, but it runs with the launch configuration of the bench's timed rounds
+    # (18 organizations on the GPU): 8-row tiles, the reduced decoder grid
+    for eng in R.eng.values():
+        eng.h.set_row_tile(roundloop.row_tile_for(18))
+        eng.h.set_decoder_blocks(roundloop.decoder_blocks_for(18))
     R.round0()
     R.run_round(1)
     R.sync()

@@ -286,3 +286,24 @@ def test_ctypes_signatures_match_the_header():
                                                                                                    len(fn.argtypes))
         checked += 1
     assert checked > 40
+
+
+def test_bench_roofline_inputs_parse():
+    """bench.py's roofline block reads the committed ncu raw page (profiles/r2_ncu_raw_fused.csv) at run time: every
+    kernel of the fused step must be found in it with non-zero DRAM / L2->SM bytes, and the per-class algorithmic bytes
+    follow SURVEY.md section 8d (1040 B per decoder target, 28 + 4 B per Adam parameter)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    per = bench.ncu_per_kernel()
+    for cls, names in bench.CLASS_KERNEL.items():
+        kern = names[1]  # the default (register-load) form
+        assert kern in per, (cls, kern, sorted(per))
+        assert per[kern]["launches"] >= 1 and per[kern]["us"] > 0 and per[kern]["l2_to_sm_bytes"] > 0
+    b = bench.step_algorithmic_bytes(t_batch=1000.0, d_batch=100.0, n_seg_t=50, n_seg_d=10, B=500, n_params=10)
+    assert b["decoder_loss_dz3"] == 1000 * (4 * 256 + 16) + 4 * 500 * 256 * 2
+    assert b["clip_adam"] == 32 * 10 and b["grad_norm"] == 40
+    with pytest.raises(FileNotFoundError):
+        bench.ncu_per_kernel(os.path.join(ROOT, "profiles", "does_not_exist.csv"))

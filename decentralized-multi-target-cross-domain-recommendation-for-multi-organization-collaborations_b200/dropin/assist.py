@@ -174,9 +174,18 @@ class Assist:
             shape = (cfg['num_items']['target'], cfg['num_users']['target'])
         else:
             raise ValueError('Not valid data mode')
+        pins = self.__dict__.setdefault('_F_pins', {})
         for k, F in F_next.items():
             ref = st.y[k]
             self._F_dev[(iter, k)] = F
-            self.organization_output[iter][k] = csr_matrix(
-                (E.to_host(F).numpy(), ref.indices_host.astype(np.int32), ref.indptr_host.astype(np.int32)), shape=shape)
+            if 'dmt_sync' in cfg and cfg['dmt_sync']:
+                self.organization_output[iter][k] = csr_matrix(
+                    (E.to_host(F).numpy(), ref.indices_host.astype(np.int32, copy=False),
+                     ref.indptr_host.astype(np.int32, copy=False)), shape=shape, copy=False)
+            else:
+                # the host copy of F_t travels on the side stream and is materialised on first read: the driver reads
+                # the test split every round (its test() loop), the train split only through make_dataset, which takes
+                # the device copy above
+                self.organization_output[iter][k] = _org_mod.lazy_csr(F, ref.indices_host, ref.indptr_host, shape,
+                                                                      pins.setdefault(k, {}))
         return

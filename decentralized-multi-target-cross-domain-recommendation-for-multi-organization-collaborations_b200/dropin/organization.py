@@ -127,6 +127,42 @@ class LazyCSR(csr_matrix):
         return (csr_matrix, ((self.data, self.indices, self.indptr), self.shape))
 
 
+def lazy_csr(vec_dev, indices_host, indptr_host, shape, slot, wait_stream=None):
+    """A LazyCSR over `vec_dev` (device fp32 vector in the CSR's storage order): the device->host copy is enqueued on the
+    side stream behind `wait_stream` (default: the current stream) into `slot['pin']`, a persistent pinned buffer that
+    consecutive outputs of the same size share (an earlier, still unread output gets its values first); nobody waits."""
+    dev = vec_dev.device
+    n = vec_dev.numel()
+    if slot.get('pin') is None or slot['pin'].numel() != n:
+        slot['pin'] = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        slot['last'] = None
+    prev = slot['last']() if slot.get('last') is not None else None
+    if prev is not None:
+        prev.data
+    src = wait_stream if wait_stream is not None else torch.cuda.current_stream(dev)
+    ready = src.record_event()
+    d2h = _d2h_stream(str(dev))
+    with torch.cuda.stream(d2h):
+        d2h.wait_event(ready)
+        slot['pin'].copy_(vec_dev, non_blocking=True)
+        done = d2h.record_event()
+    vec_dev.record_stream(d2h)
+    E.XFER["d2h"] += n * 4
+    host = np.empty(n, dtype=np.float32)
+    m = LazyCSR((host, indices_host.astype(np.int32, copy=False), indptr_host.astype(np.int32, copy=False)),
+                shape=shape, copy=False)
+    pin = slot['pin']
+    dest = m.__dict__['_dmt_data']  # the array scipy actually kept
+
+    def force():
+        done.synchronize()
+        np.copyto(dest, pin.numpy())
+
+    m.__dict__['_dmt_force'] = force
+    slot['last'] = weakref.ref(m)
+    return m
+
+
 class LazyStateDict(dict):
     """state_dict whose tensors are still on the organization's stream; materialised on first read."""
 

@@ -198,6 +198,32 @@ class FastEpochLayout:
         self.n_d = int(dl.sum())
 
 
+class RoundLayout:
+    """All local epochs of one organization's round from ONE FastEpochLayout pass over the concatenated permutations
+    (the per-epoch layouts of a round used to cost 360 numpy passes per 18-organization round, ~100 ms of host time
+    next to a 200 ms GPU round: a slower host made the round host-bound). Per-epoch views are slices:
+    rows [row_edges[e], row_edges[e+1]), local batch offsets off_local[e], entry counts n_t[e] / n_d[e]."""
+
+    def __init__(self, perms, batch_size, d_len, t_len, n_rows, n_epochs):
+        L = FastEpochLayout(perms, batch_size, d_len, t_len, epoch_len=n_rows)
+        self.whole = L
+        self.n_epochs = n_epochs
+        self.nb_epoch = -(-n_rows // batch_size)                      # batches per epoch
+        G = L.row_off.astype(np.int64)
+        idx = np.arange(self.nb_epoch + 1)[None, :] + (np.arange(n_epochs) * self.nb_epoch)[:, None]
+        self.row_edges = G[idx[:, 0]].tolist() + [int(G[-1])]          # first row of every epoch (+ end)
+        self.off_local = (G[idx] - G[idx[:, :1]]).astype(np.int32)     # [n_epochs x (nb_epoch + 1)]
+        self.rows = L.rows.astype(np.int32)
+        self.off_global = L.row_off
+        ct = np.concatenate([[0], np.cumsum(t_len[L.rows], dtype=np.int64)])
+        cd = np.concatenate([[0], np.cumsum(d_len[L.rows], dtype=np.int64)])
+        e = np.asarray(self.row_edges)
+        self.n_t = (ct[e[1:]] - ct[e[:-1]]).tolist()
+        self.n_d = (cd[e[1:]] - cd[e[:-1]]).tolist()
+        self.n_t_total, self.n_d_total = L.n_t, L.n_d
+        self.n_batches = len(L.active)
+
+
 def decoder_default():
     """Decoder form of new engines: DMT_DECODER=gather|tc. Default gather (row-gather SDDMM + segmented reductions):
     measured on B200 at ML1M shape (500-row batches, 3.7 % dense targets) it is ~1.5x faster per step than the

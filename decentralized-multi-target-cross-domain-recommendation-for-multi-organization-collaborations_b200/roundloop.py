@@ -149,6 +149,7 @@ class AssistRounds:
         self.host_gen.manual_seed(seed * 7919 + rank)
         self.round_losses = {}
         self._up_stream = None
+        self._pool = None
         self._pending_uploads = []
         self._held_uploads = []
 
@@ -207,24 +208,25 @@ class AssistRounds:
                 st.privatize(self.residual[k], self.privacy[0], self.privacy[1], E.he_seed(self.seed, t, i, 1 << 22))
         loss_bufs = {}
         layouts, rows_dev, off_dev, glob_dev = {}, {}, {}, {}
-        # (1) host-only preparation of every organization's epochs: no CUDA call, so it overlaps the previous round that
-        #     the GPU is still executing (run_round never synchronises)
-        host = {}
+        # (1) host-only preparation of every organization's round: no CUDA call, so it overlaps the previous round that
+        #     the GPU is still executing (run_round never synchronises). One layout pass per organization and round,
+        #     organizations spread over a few host threads (numpy and torch.randperm release the GIL).
         need_glob = self.whole_round or self.group is not None
-        for org in self.my_orgs:
+
+        def prepare(org):
             eng = self.eng[org]
-            self.host_gen.manual_seed(E.he_seed(self.seed, org, t, 1 << 21) & (2 ** 63 - 1))
-            lays = [E.FastEpochLayout(torch.randperm(self.n_rows, generator=self.host_gen).numpy(), self.batch_rows,
-                                      eng.d_len, eng.t_len) for _ in range(self.local_epochs)]
-            layouts[org] = lays
-            rows_np = np.concatenate([l.rows for l in lays]).astype(np.int32)
-            off_np = np.concatenate([l.row_off for l in lays]).astype(np.int32)
-            glob_np = None
-            if need_glob:
-                base = np.cumsum([0] + [len(l.rows) for l in lays[:-1]])
-                glob_np = np.concatenate([l.row_off[:-1] + b for l, b in zip(lays, base)] +
-                                         [np.array([sum(len(l.rows) for l in lays)])]).astype(np.int32)
-            host[org] = (rows_np, off_np, glob_np)
+            g = torch.Generator()
+            g.manual_seed(E.he_seed(self.seed, org, t, 1 << 21) & (2 ** 63 - 1))
+            perms = np.concatenate([torch.randperm(self.n_rows, generator=g).numpy() for _ in range(self.local_epochs)])
+            return E.RoundLayout(perms, self.batch_rows, eng.d_len, eng.t_len, self.n_rows, self.local_epochs)
+
+        if len(self.my_orgs) > 1:
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=min(8, len(self.my_orgs)))
+            layouts = dict(zip(self.my_orgs, self._pool.map(prepare, self.my_orgs)))
+        else:
+            layouts = {org: prepare(org) for org in self.my_orgs}
         # (2) uploads from pinned staging on a side stream: not ordered behind the compute streams, so neither the
         #     copies nor the host wait for the previous round to drain
         self._reap_uploads()
@@ -232,13 +234,15 @@ class AssistRounds:
         held = []
         with torch.cuda.stream(up):
             for org in self.my_orgs:
-                rows_np, off_np, glob_np = host[org]
-                rows_dev[org] = self._upload(rows_np)
-                off_dev[org] = self._upload(off_np)
-                held += [rows_dev[org], off_dev[org]]
-                if glob_np is not None:
-                    glob_dev[org] = self._upload(glob_np)
+                lay = layouts[org]
+                rows_dev[org] = self._upload(lay.rows)
+                held.append(rows_dev[org])
+                if need_glob:
+                    glob_dev[org] = self._upload(lay.off_global)
                     held.append(glob_dev[org])
+                else:
+                    off_dev[org] = self._upload(lay.off_local.ravel())
+                    held.append(off_dev[org])
         uploaded = up.record_event()
         torch.cuda.current_stream().wait_event(uploaded)
         # (3) device side: fresh parameters, targets, loss buffers
@@ -247,52 +251,38 @@ class AssistRounds:
             self.gen.manual_seed(E.he_seed(self.seed, org, t, 1 << 20) & (2 ** 63 - 1))
             flat0 = init_flat_params(eng.n_enc, eng.n_dec, self.H1, self.H2, self.device, self.gen)
             eng.set_round(flat0, self.residual["train"])
-            loss_bufs[org] = torch.zeros(sum(len(l.active) for l in layouts[org]), device=self.device)
+            loss_bufs[org] = torch.zeros(layouts[org].n_batches, device=self.device)
             eng.h.wait_current()
             eng._keep_alive += [loss_bufs[org]]
         self._held_uploads = held
         same_rows = len({len(rows_dev[o]) for o in self.my_orgs}) == 1
         if self.group is not None and same_rows:
             # whole round of every organization: one plan per organization + ONE graph launch for all steps
-            offs, nts, nds, seeds = [], [], [], []
-            for org in self.my_orgs:
-                lays = layouts[org]
-                off_dev[org] = glob_dev[org]
-                offs.append(off_dev[org])
-                nts.append(sum(l.n_t for l in lays))
-                nds.append(sum(l.n_d for l in lays))
-                seeds.append(E.he_seed(self.seed, org, t, 0))
-            n_batches = len(host[self.my_orgs[0]][2]) - 1
-            self.group.train([rows_dev[o] for o in self.my_orgs], offs, len(rows_dev[self.my_orgs[0]]), n_batches,
-                             nts, nds, seeds, batch_loss=[loss_bufs[o] for o in self.my_orgs], **self.hp)
+            lays = [layouts[o] for o in self.my_orgs]
+            self.group.train([rows_dev[o] for o in self.my_orgs], [glob_dev[o] for o in self.my_orgs],
+                             len(rows_dev[self.my_orgs[0]]), lays[0].n_batches, [l.n_t_total for l in lays],
+                             [l.n_d_total for l in lays], [E.he_seed(self.seed, o, t, 0) for o in self.my_orgs],
+                             batch_loss=[loss_bufs[o] for o in self.my_orgs], **self.hp)
             self._finish_round_local(t, loss_bufs)
             return
         if self.whole_round:
             # one plan + one graph launch per organization for all local epochs of the round
             for org in self.my_orgs:
-                lays = layouts[org]
-                goff = glob_dev[org]
-                self.eng[org].h.train_epoch(rows_dev[org], goff, sum(l.n_t for l in lays), sum(l.n_d for l in lays),
-                                            keep=None, seed=E.he_seed(self.seed, org, t, 0),
-                                            epoch_loss=loss_bufs[org], **self.hp)
+                lay = layouts[org]
+                self.eng[org].h.train_epoch(rows_dev[org], glob_dev[org], lay.n_t_total, lay.n_d_total, keep=None,
+                                            seed=E.he_seed(self.seed, org, t, 0), epoch_loss=loss_bufs[org], **self.hp)
             self._finish_round_local(t, loss_bufs)
             return
         # per-organization graphs, epoch-major enqueue: every organization's stream gets work early, so the GPU never
         # waits for the host to reach the last organization
-        r0 = {org: 0 for org in self.my_orgs}
-        o0 = dict(r0)
-        l0 = dict(r0)
         for e in range(self.local_epochs):
             for org in self.my_orgs:
-                lay = layouts[org][e]
-                nb = len(lay.row_off) - 1
-                self.eng[org].h.train_epoch(rows_dev[org][r0[org]:r0[org] + len(lay.rows)],
-                                            off_dev[org][o0[org]:o0[org] + nb + 1], lay.n_t, lay.n_d, keep=None,
-                                            seed=E.he_seed(self.seed, org, t, 0),  # the step counter varies the draw
-                                            epoch_loss=loss_bufs[org][l0[org]:l0[org] + nb], **self.hp)
-                r0[org] += len(lay.rows)
-                o0[org] += nb + 1
-                l0[org] += nb
+                lay = layouts[org]
+                nb = lay.nb_epoch
+                self.eng[org].h.train_epoch(rows_dev[org][lay.row_edges[e]:lay.row_edges[e + 1]],
+                                            off_dev[org][e * (nb + 1):(e + 1) * (nb + 1)], lay.n_t[e], lay.n_d[e],
+                                            keep=None, seed=E.he_seed(self.seed, org, t, 0),  # the step counter varies the draw
+                                            epoch_loss=loss_bufs[org][e * nb:(e + 1) * nb], **self.hp)
         self._finish_round_local(t, loss_bufs)
 
     def _finish_round_local(self, t, loss_bufs):

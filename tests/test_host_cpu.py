@@ -307,3 +307,28 @@ def test_bench_roofline_inputs_parse():
     assert b["clip_adam"] == 32 * 10 and b["grad_norm"] == 40
     with pytest.raises(FileNotFoundError):
         bench.ncu_per_kernel(os.path.join(ROOT, "profiles", "does_not_exist.csv"))
+
+
+def test_round_layout_equals_per_epoch_layouts():
+    """engine.RoundLayout (one pass per organization and round) slices into exactly the per-epoch FastEpochLayouts."""
+    import dmtcdr_b200  # noqa: F401
+    from dmtcdr_b200 import engine as E
+
+    rng = np.random.default_rng(4)
+    for n_rows, bs in ((1037, 100), (500, 500), (6040, 500), (7, 3)):
+        d_len = rng.integers(0, 3, n_rows).astype(np.int64)
+        t_len = rng.integers(0, 4, n_rows).astype(np.int64)
+        n_ep = 5
+        perms = [rng.permutation(n_rows) for _ in range(n_ep)]
+        R = E.RoundLayout(np.concatenate(perms), bs, d_len, t_len, n_rows, n_ep)
+        per = [E.FastEpochLayout(p, bs, d_len, t_len) for p in perms]
+        nb = R.nb_epoch
+        assert R.n_batches == sum(len(l.active) for l in per)
+        assert (R.n_t_total, R.n_d_total) == (sum(l.n_t for l in per), sum(l.n_d for l in per))
+        for e, l in enumerate(per):
+            assert np.array_equal(R.rows[R.row_edges[e]:R.row_edges[e + 1]], l.rows)
+            assert np.array_equal(R.off_local[e], l.row_off) and len(l.row_off) == nb + 1
+            assert (R.n_t[e], R.n_d[e]) == (l.n_t, l.n_d)
+            assert R.whole.active[e * nb:(e + 1) * nb] == l.active
+        glob = np.concatenate([[0], np.cumsum([c for l in per for c in l.batch_rows])])
+        assert np.array_equal(R.off_global, glob)

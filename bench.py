@@ -395,6 +395,16 @@ def run_ours(args):
         eager = run_e2e(args, data, rank, world, dev, state_dicts=True, n_steps=2)
         e2e["e2e_with_state_dicts"] = {k: eager[k] for k in ("value", "ms_per_step", "d2h_bytes_per_step", "state_dicts")}
 
+    # the side blocks below run in a clean state: the headline's engines (18 organizations' parameters, plans and
+    # graphs) and whatever the e2e experiments left in torch's caching allocator are released first
+    line_cfg = {"orgs_per_rank": len(rounds.my_orgs),
+                "decoder": rounds.eng[rounds.my_orgs[0]].decoder if rounds.my_orgs else None,
+                "step_fanout": bool(rounds.fanout)}
+    if world == 1:
+        import gc
+        rounds.close()
+        gc.collect()
+        torch.cuda.empty_cache()
     mf = run_mf_joint(data, dev) if (rank == 0 and world == 1) else None
     nmf = None
     if rank == 0 and world == 1 and args.configs != "none":
@@ -405,7 +415,6 @@ def run_ours(args):
     # the other BASELINE.json configurations, as extra blocks of the line (N=1 only; each with its own CPU leg)
     more = None
     if rank == 0 and world == 1 and args.configs != "none":
-        rounds.close()
         more = {}
         for key, control, data_name in OTHER_CONFIGS:
             if args.configs in ("all", key):
@@ -440,9 +449,8 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "control_name": CONTROL, "local_epochs": args.local_epochs,
-                       "orgs_per_rank": len(rounds.my_orgs), "parallelism": "org-sharded x{}".format(world),
-                       "decoder": rounds.eng[rounds.my_orgs[0]].decoder if rounds.my_orgs else None,
-                       "step_fanout": bool(rounds.fanout),
+                       "orgs_per_rank": line_cfg["orgs_per_rank"], "parallelism": "org-sharded x{}".format(world),
+                       "decoder": line_cfg["decoder"], "step_fanout": line_cfg["step_fanout"],
                        "l2_policy": "inputs larger than L2: per-round working set (18 x 17 MB parameters+moments, "
                                     "2 x 72 MB prediction matrices, plans) exceeds 126 MB"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,

@@ -222,6 +222,45 @@ class LazyStateDict(dict):
         return (dict, (dict(self._force()),))
 
 
+_LAYOUTS = {}
+_LAYOUT_POOL = None
+
+
+def _build_round_layout(seed, n_own, n_epochs, bs, d_len, t_len):
+    g = torch.Generator()
+    g.manual_seed(seed)
+    perms = np.concatenate([torch.randperm(n_own, generator=g).numpy() for _ in range(n_epochs)])
+    return E.FastEpochLayout(perms, bs, d_len, t_len, epoch_len=n_own)
+
+
+def _layout_key(org, it, n_own, n_epochs, bs):
+    return (int(cfg['seed']), int(org), int(it), int(n_own), int(n_epochs), int(bs))
+
+
+def _prefetch_round_layout(org, it, n_own, n_epochs, bs, d_len, t_len):
+    """Build the whole-round batch layout of (organization, round) on a background thread (numpy and torch.randperm
+    release the GIL): the same permutations as the foreground path — the host generator of _seeded_generators is
+    seeded per (seed, organization, round) — so results do not depend on whether the prefetch was used."""
+    global _LAYOUT_POOL
+    key = _layout_key(org, it, n_own, n_epochs, bs)
+    if key in _LAYOUTS:
+        return
+    if _LAYOUT_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _LAYOUT_POOL = ThreadPoolExecutor(max_workers=2)
+    if len(_LAYOUTS) > 256:
+        _LAYOUTS.clear()
+    seed = E.he_seed(cfg['seed'], org, it, 1 << 21) & (2 ** 63 - 1)
+    _LAYOUTS[key] = _LAYOUT_POOL.submit(_build_round_layout, seed, n_own, n_epochs, bs, d_len, t_len)
+
+
+def _round_layout(org, it, n_own, n_epochs, bs, d_len, t_len):
+    fut = _LAYOUTS.pop(_layout_key(org, it, n_own, n_epochs, bs), None)
+    if fut is not None:
+        return fut.result()
+    return _build_round_layout(E.he_seed(cfg['seed'], org, it, 1 << 21) & (2 ** 63 - 1), n_own, n_epochs, bs, d_len, t_len)
+
+
 _GENS = {}
 
 
@@ -407,8 +446,11 @@ class Organization:
                 losses.append(lo)
             loss_all = torch.cat(losses)
         elif eng.plan_epochs >= n_epochs > 1:
-            perms = np.concatenate([torch.randperm(n_own, generator=host_gen).numpy() for _ in range(n_epochs)])
-            lay = E.FastEpochLayout(perms, bs, eng.d_len, eng.t_len, epoch_len=n_own)
+            # the round's layout depends only on (seed, organization, round): it was prepared by the background worker
+            # while the GPU ran the previous round (or is built now), and the next round's is requested right away
+            lay = _round_layout(self.organization_id, iter, n_own, n_epochs, bs, eng.d_len, eng.t_len)
+            if iter + 1 <= cfg['global']['num_epochs']:
+                _prefetch_round_layout(self.organization_id, iter + 1, n_own, n_epochs, bs, eng.d_len, eng.t_len)
             layouts.append(lay)
             loss_all = torch.zeros(len(lay.active), device=dev)
             eng.enqueue_round(lay, E.he_seed(cfg['seed'], self.organization_id, iter, 0), hp=hp, loss_out=loss_all)

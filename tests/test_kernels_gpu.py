@@ -276,8 +276,8 @@ def test_combine_and_fit_kernels_vs_golden(nat, case):
 def test_device_lbfgs_vs_torch_lbfgs(nat, case, modes):
     """dmt_assist_fit (the whole L-BFGS fit as a chain of launches, optimizer state on the device) against
     torch.optim.LBFGS(lr=0.1) x 10 step() calls driving the oracle's differentiable models.assist expression on the
-    CPU — the reference's fit (src/assist.py:118-129, src/utils.py:255-256) on the same owner view: same objective
-    (1e-6 relative), fitted rates / softmax weights within 2e-2 (see the comment at the assertions)."""
+    CPU — the reference's fit (src/assist.py:118-129, src/utils.py:255-256) on the same owner view: objective not worse
+    than torch's and within 1e-4 of it, fitted rates / softmax weights within 2e-2 (see the comment at the assertions)."""
     ar_mode, aw_mode = modes
     fx = Fixture(case)
     m = fx.meta
@@ -325,13 +325,15 @@ def test_device_lbfgs_vs_torch_lbfgs(nat, case, modes):
         # softmax(w) is what the model uses (w itself is only defined up to a common shift). Both optimizers stop on
         # |loss - prev_loss| < 1e-9, which in a flat valley (the weight-only fit at ML shape) is decided by the last
         # bit of the loss, and the torch side of this comparison runs on the host CPU: the two runs may stop a few
-        # iterations apart. The sharp, host-independent statement is the objective: equal to 1e-6 relative. The
-        # parameters are bounded at 2e-2 here (the walk along such a valley measured 4e-3); the 2e-3 bound on fitted
-        # rates / weights is held against the reference's own outputs by the round fixtures (test_dropin_gpu.py).
+        # iterations apart (measured: the device run went on to an objective 8e-6 lower, weights 4e-3 apart). The
+        # host-independent statement is the objective: not worse than torch's (1e-6 relative) and within 1e-4 of it.
+        # The parameters are bounded at 2e-2 here; the 2e-3 bound on fitted rates / weights is held against the
+        # reference's own outputs by the round fixtures (test_dropin_gpu.py).
         with torch.no_grad():
             _, l_dev = om.assist_forward(got[:n_rate], got[n_rate:], hi, Oi, ii, ti, m["target_mode"])
             _, l_ref = om.assist_forward(rate, w, hi, Oi, ii, ti, m["target_mode"])
-        assert abs(float(l_dev) - float(l_ref)) <= 1e-6 * abs(float(l_ref)), (i, float(l_dev), float(l_ref))
+        l_dev, l_ref = float(l_dev), float(l_ref)
+        assert l_dev <= l_ref * (1 + 1e-6) and abs(l_dev - l_ref) <= 1e-4 * abs(l_ref), (i, l_dev, l_ref)
         e_rate = rel_err(got[:n_rate], rate.detach())
         e_w = rel_err(torch.softmax(got[n_rate:], -1), torch.softmax(w.detach(), -1))
         assert e_rate < 2e-2, (i, "rate", e_rate, got[:n_rate][:5], rate.detach()[:5])

@@ -40,9 +40,10 @@ def decoder_blocks_for(n_orgs):
 
 def row_tile_for(n_orgs):
     """Batch rows per CTA of the fused step's row kernels by the organizations that share the GPU: 4 shortens a lone
-    organization's step (19 + 16 -> 14 + 12 us) and pays up to 3 organizations per GPU; measured ms per ML1M-shape
-    round, 8 -> 4 rows: 2 organizations 30.5 -> 28.6, 5: 53.6 -> 55.4, 9: 96.4 -> 100.9, 18: 197.7 -> 205.7."""
-    return 4 if n_orgs <= 3 else 8
+    organization's step (19 + 16 -> 14 + 12 us) and pays for one or two organizations per GPU; measured ms per
+    ML1M-shape round, 8 -> 4 rows: 2 organizations 30.5 -> 28.6, 3: 35.8 -> 36.0, 5: 53.6 -> 55.4, 9: 96.4 -> 100.9,
+    18: 197.7 -> 205.7."""
+    return 4 if n_orgs <= 2 else 8
 
 
 # device memory the whole-round plans of a rank may take (bytes); DMT_WHOLE_ROUND=0|1 overrides

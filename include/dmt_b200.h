@@ -297,7 +297,7 @@ int dmt_org_set_gather_mode(dmt_org_t* org, int mode);
 int dmt_org_set_pdl(dmt_org_t* org, int on);
 /* Batch rows per CTA of the row-local forward / backward kernels of the fused step at 500-row batches (4, 8 or 16;
  * default 8). With 4 rows per CTA two warps share every row's encoder entries and the per-CTA dense work halves: the
- * kernels take 14 / 12 us instead of 19 / 16 us (ML1M shape), which shortens the round of a rank that holds <= 3
+ * kernels take 14 / 12 us instead of 19 / 16 us (ML1M shape), which shortens the round of a rank that holds one or two
  * organizations (28.6 vs 30.5 ms) and lengthens it when more organizations share the GPU (twice the CTAs and weight
  * traffic: 18 organizations 205.7 vs 197.7 ms). Same arithmetic; the encoder sum of a row is split in two ordered
  * halves. */

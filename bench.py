@@ -510,7 +510,10 @@ def hbm_bound_case(dev, hbm):
     return {"kernel": "ae_decoder_fwd_kernel<2>", "shape": "512 rows x 2048 distinct targets over 1.1M columns (W4 1.13 GB >> L2)",
             "ms_per_launch": ms, "algorithmic_bytes_per_launch": bytes_, "achieved": ach, "peak": hbm,
             "frac": ach / hbm, "unit": "GB/s",
-            "traffic": 1.101e9, "traffic_source": "profiles/r1_ncu_raw_decoder_hbm.csv: dram read 1.088 GB + write 13 MB per launch"}
+            "traffic": ncu_per_kernel(os.path.join(ROOT, "profiles", "r1_ncu_raw_decoder_hbm.csv"))[
+                "ae_decoder_fwd_kernel"]["dram_bytes"],
+            "traffic_source": "profiles/r1_ncu_raw_decoder_hbm.csv (ncu --set full of this kernel on this shape: dram read + "
+                              "write per launch, parsed at bench time)"}
 
 
 def tc_decoder_case(y_csr, dev, prof_gather, prof_tc):

@@ -1,9 +1,10 @@
 """Organization -> rank sharding and the per-round exchange of organization outputs.
 
 The reference passes the K prediction matrices around as Python lists inside one process
-(src/train_recsys_assist.py:166-172). Here rank r owns the contiguous block of organizations
-[r*c, (r+1)*c), c = ceil(K / world); after ``predict`` each rank holds its own rows of the organization-major
-matrix O[split] ([world*c x nnz], rows >= K are padding) and ONE in-place all-gather per split publishes the rest.
+(src/train_recsys_assist.py:166-172). Here ``assign_orgs`` spreads the organizations over the ranks (balanced by
+count, then by work); rank r's organizations occupy rows [r*c, (r+1)*c) of the organization-major matrix O[split]
+([world*c x nnz], c = most organizations any rank holds, unused rows are padding), so after ``predict`` ONE in-place
+all-gather per split publishes everybody's rows.
 NCCL over NVLink on the GPU box; gloo on CPU for the world_size-2 tests.
 """
 from __future__ import annotations

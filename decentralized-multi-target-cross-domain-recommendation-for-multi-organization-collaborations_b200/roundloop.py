@@ -1,10 +1,11 @@
 """Device-resident assistance rounds with organizations sharded over ranks.
 
 One process per GPU. Every rank keeps the global CSR structure, ground truth and current global prediction F_t;
-organization k (its data column block, parameters, optimizer state, epoch plans and CUDA graph) lives on rank
-``k // ceil(K / world)`` (contiguous blocks). Inside a round the ranks share nothing; the only exchange is the K prediction vectors after
-``predict`` (reference: plain Python list passing, src/train_recsys_assist.py:166-172; src/assist.py:81-84):
-an NCCL all-gather of the [K x nnz] organization-major matrix rows over NVLink. After it every
+organization k (its data column block, parameters, optimizer state, epoch plans and CUDA graph) lives on the rank
+``dist.assign_orgs`` gives it (balanced by count, then by work). Inside a round the ranks share nothing; the only
+exchange is the K prediction vectors after ``predict`` (reference: plain Python list passing,
+src/train_recsys_assist.py:166-172; src/assist.py:81-84): an in-place NCCL all-gather of the rank-blocked
+organization-major matrix rows over NVLink. After it every
 rank runs the same (cheap, O(K nnz)) ``update`` so F_{t} is replicated without a second collective.
 """
 from __future__ import annotations

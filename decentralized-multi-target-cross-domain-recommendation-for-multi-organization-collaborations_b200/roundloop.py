@@ -40,11 +40,13 @@ def decoder_blocks_for(n_orgs):
 
 
 def row_tile_for(n_orgs):
-    """Batch rows per CTA of the fused step's row kernels by the organizations that share the GPU: 4 shortens a lone
-    organization's step (19 + 16 -> 14 + 12 us) and pays for one or two organizations per GPU; measured ms per
-    ML1M-shape round, 8 -> 4 rows: 2 organizations 30.5 -> 28.6, 3: 35.8 -> 36.0, 5: 53.6 -> 55.4, 9: 96.4 -> 100.9,
-    18: 197.7 -> 205.7."""
-    return 4 if n_orgs <= 2 else 8
+    """Batch rows per CTA of the fused step's row kernels: always 8. Four rows per CTA (two warps per encoder row)
+    shorten a lone organization's step (19 + 16 -> 14 + 12 us) and the round of a rank with one or two organizations
+    (30.5 -> 28.6 ms; three: 35.8 vs 36.0; five and more: slower), but the tile size changes the grouping of the
+    encoder and bias-gradient sums, so choosing it by the organizations a rank happens to hold would make the result
+    depend on the sharding in the last bit (scripts/check_sharded_dropin.py caught exactly that). An 8-GPU run is
+    bounded by its three-organization ranks anyway. `dmt_org_set_row_tile` / DMT_STREAM_ROWS=4 remain for explicit use."""
+    return 8
 
 
 # device memory the whole-round plans of a rank may take (bytes); DMT_WHOLE_ROUND=0|1 overrides

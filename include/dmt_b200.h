@@ -299,8 +299,9 @@ int dmt_org_set_pdl(dmt_org_t* org, int on);
  * default 8). With 4 rows per CTA two warps share every row's encoder entries and the per-CTA dense work halves: the
  * kernels take 14 / 12 us instead of 19 / 16 us (ML1M shape), which shortens the round of a rank that holds one or two
  * organizations (28.6 vs 30.5 ms) and lengthens it when more organizations share the GPU (twice the CTAs and weight
- * traffic: 18 organizations 205.7 vs 197.7 ms). Same arithmetic; the encoder sum of a row is split in two ordered
- * halves. */
+ * traffic: 18 organizations 205.7 vs 197.7 ms). Same arithmetic, but the encoder sum of a row is split in two ordered
+ * halves and the bias-gradient partials group four rows: results differ from the 8-row tile in the last bit, so the
+ * Python layers never switch it by themselves (results must not depend on how organizations are sharded). */
 int dmt_org_set_row_tile(dmt_org_t* org, int rows);
 int dmt_org_gather_mode(const dmt_org_t* org);
 /* How one iteration of the batch loop (src/organization.py:149-162) is cut into launches. mode 1 (default whenever

@@ -332,3 +332,33 @@ def test_round_layout_equals_per_epoch_layouts():
             assert R.whole.active[e * nb:(e + 1) * nb] == l.active
         glob = np.concatenate([[0], np.cumsum([c for l in per for c in l.batch_rows])])
         assert np.array_equal(R.off_global, glob)
+
+
+def test_dropin_round_layout_prefetch_is_deterministic():
+    """The drop-in prepares the NEXT round's batch layout on a background thread (dropin/organization.py:
+    _prefetch_round_layout): prefetched and foreground layouts are the same object-for-object, and both equal the
+    permutations the per-(seed, organization, round) host generator draws."""
+    import dmtcdr_b200
+    from dmtcdr_b200 import engine as E
+    from dmtcdr_b200.config import make_cfg
+
+    make_cfg("ML100K_user_explicit_ae_0_genre_assist_constant-0.1_constant", device="cpu", seed=3)
+    dmtcdr_b200.use_dropin()
+    import organization as org_mod
+
+    rng = np.random.default_rng(0)
+    n_own, n_ep, bs = 333, 4, 50
+    d_len = rng.integers(0, 3, n_own).astype(np.int64)
+    t_len = rng.integers(0, 5, n_own).astype(np.int64)
+    org_mod._prefetch_round_layout(2, 5, n_own, n_ep, bs, d_len, t_len)
+    a = org_mod._round_layout(2, 5, n_own, n_ep, bs, d_len, t_len)      # takes the prefetched future
+    b = org_mod._round_layout(2, 5, n_own, n_ep, bs, d_len, t_len)      # builds it in the foreground
+    g = torch.Generator()
+    g.manual_seed(E.he_seed(3, 2, 5, 1 << 21) & (2 ** 63 - 1))
+    perms = np.concatenate([torch.randperm(n_own, generator=g).numpy() for _ in range(n_ep)])
+    c = E.FastEpochLayout(perms, bs, d_len, t_len, epoch_len=n_own)
+    for x in (a, b):
+        assert np.array_equal(x.rows, c.rows) and np.array_equal(x.row_off, c.row_off)
+        assert x.active == c.active and (x.n_t, x.n_d) == (c.n_t, c.n_d)
+    other = org_mod._round_layout(2, 6, n_own, n_ep, bs, d_len, t_len)
+    assert not np.array_equal(other.rows, c.rows)

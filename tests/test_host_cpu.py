@@ -362,3 +362,26 @@ def test_dropin_round_layout_prefetch_is_deterministic():
         assert x.active == c.active and (x.n_t, x.n_d) == (c.n_t, c.n_d)
     other = org_mod._round_layout(2, 6, n_own, n_ep, bs, d_len, t_len)
     assert not np.array_equal(other.rows, c.rows)
+
+
+def test_reference_arm_harness_runs_the_unmodified_reference(tmp_path):
+    """baseline/ref_arm.py (the bench's `--impl reference` and `cpu_baseline` leg) imports the UNMODIFIED reference
+    (baseline/_ref/src, vendored by __graft_entry__.build(), or /root/reference/src in the build container) and times
+    its own Assist.make_dataset / Organization.train / predict / Assist.update on the host: here on the tiny Douban-shape
+    data, one step. Skipped only where no copy of the reference exists."""
+    import json as _json
+
+    if not any(os.path.exists(os.path.join(p, "organization.py"))
+               for p in (os.path.join(ROOT, "baseline", "_ref", "src"), "/root/reference/src")):
+        pytest.skip("no copy of the reference sources")
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_arm.py"), "--control",
+           "Douban_user_explicit_ae_0_genre_assist_constant-0.3_constant", "--data", "tiny-Douban", "--device", "cpu",
+           "--threads", "2", "--steps", "1", "--warmup", "0", "--budget-s", "30"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    lines = [l for l in out.stdout.splitlines() if l.startswith("REF_ARM_JSON ")]
+    assert out.returncode == 0 and lines, (out.stdout[-500:], out.stderr[-1500:])
+    res = _json.loads(lines[-1][len("REF_ARM_JSON "):])
+    assert res["kind"] == "reference" and res["cores"] == 2 and res["steps_done"] == 1
+    assert res["value"] > 0 and res["round_s"] > 0
+    for k in ("t_make_dataset_s", "t_train_epoch_s", "t_predict_s", "t_update_s"):
+        assert res[k] > 0, k
